@@ -1,0 +1,313 @@
+// Device-resident Metropolis-within-Gibbs sampler for the sim-only SEPIA model.
+//
+// Replaces SepiaModel.mcmc_step / do_mcmc / logPost (SURVEY.md 8a row a5, Appendix A.4-A.6,
+// A.10; driven from /root/reference/src/model.py:234-235).  One step is four launches:
+//   plan      (1 thread / chain)   draws every candidate of the step from the uniform stream
+//                                  (or copies them from replay tables): candidates, bounds and the
+//                                  PropMH correction depend only on start-of-step values.
+//   sweep     (1 CTA / (PC,chain)) the d betaU sites, lamUz and lamWs of one PC, sequentially;
+//                                  each site is one fused cov+Cholesky evaluation.  PCs are
+//                                  independent for these sites (log-lik is a sum of per-PC terms,
+//                                  priors are per element), so all PCs of all chains run at once.
+//   wos_eval  (1 CTA / (PC,chain)) per-PC terms under the candidate lamWOs
+//   finalize  (1 thread / chain)   lamWOs accept/reject, log-posterior, record the draw
+#include "ggp_chol.cuh"
+#include "../../include/gladsgp_b200.h"
+
+namespace ggp {
+
+enum { PRIOR_UNIFORM = 0, PRIOR_GAMMA = 1, PRIOR_BETA = 2, PRIOR_NORMAL = 3 };
+enum { PROP_UNIFORM = 0, PROP_BETARHO = 1, PROP_PROPMH = 2 };
+
+__device__ inline double elem_log_prior(int kind, double a, double b, double x)
+{
+    switch (kind) {
+        case PRIOR_GAMMA: return (a - 1.0) * log(x) - b * x;
+        case PRIOR_BETA: {
+            double rho = exp(-x / 4.0);
+            if (rho > 0.999) rho = 0.999;
+            return (a - 1.0) * log(rho) + (b - 1.0) * log(1.0 - rho);
+        }
+        case PRIOR_NORMAL: {
+            double z = (x - a) / b;
+            return -0.5 * (z * z);
+        }
+        default: return 0.0;
+    }
+}
+
+struct Plan {
+    double* cand;      // [n_chains][P]
+    double* lacorr;    // [n_chains][P]
+    double* logu;      // [n_chains][P]
+    int* valid;        // [n_chains][P]
+};
+
+__global__ void plan_kernel(ggp_mcmc_args a, Plan pl, int t)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chains) return;
+    const int P = a.d * a.pu + 2 * a.pu + 1;
+    const double* th = a.theta + (size_t)c * P;
+    const double* step = a.step + (size_t)t * a.step_stride_t + (size_t)c * a.step_stride_c;
+    long long pos = a.upos ? a.upos[c] : 0;
+    const double* us = a.uniforms ? a.uniforms + (size_t)c * a.n_uniform : nullptr;
+    for (int s = 0; s < P; ++s) {
+        const size_t o = (size_t)c * P + s;
+        double cand, lac = 0.0, lu = 0.0;
+        int valid;
+        if (a.replay) {
+            const size_t ro = ((size_t)t * a.n_chains + c) * P + s;
+            cand = a.r_cand[ro];
+            lac = a.r_logacorr[ro];
+            lu = a.r_logu[ro];
+            valid = a.r_valid[ro] && !a.fixed[s];
+        } else {
+            const double x = th[s];
+            const double st = step[s];
+            const double u = us[pos++];
+            double acorr = 1.0;
+            int kind = a.prop_kind[s];
+            if (kind == PROP_PROPMH && !a.do_propMH) kind = PROP_UNIFORM;
+            if (kind == PROP_UNIFORM) {
+                cand = __dadd_rn(x, __dmul_rn(st, __dadd_rn(-0.5, u)));
+            } else if (kind == PROP_BETARHO) {
+                const double rho = __dadd_rn(exp(-x / 4.0), __dmul_rn(st, __dadd_rn(-0.5, u)));
+                cand = (rho <= 0.0) ? INFINITY : -4.0 * log(rho);
+            } else {
+                const double w = fmax(1.0, x / 3.0);
+                cand = __dadd_rn(x, __dmul_rn(w, __dadd_rn(-1.0, __dmul_rn(2.0, u))));
+                const double w1 = fmax(1.0, cand / 3.0);
+                acorr = (x > cand + w1) ? 0.0 : w / w1;
+            }
+            valid = !a.fixed[s] && (acorr > 0.0) && (cand >= a.lo[s]) && (cand <= a.hi[s]);
+            if (valid) {
+                lu = log(us[pos++]);
+                lac = log(acorr);
+            }
+        }
+        pl.cand[o] = cand;
+        pl.lacorr[o] = lac;
+        pl.logu[o] = lu;
+        pl.valid[o] = valid;
+    }
+    if (a.upos) a.upos[c] = pos;
+}
+
+// parameters of PC j under the current state, optionally with one site replaced by its candidate
+__device__ inline void gather_block_params(const ggp_mcmc_args& a, const double* th, int j, int site, double cand,
+                                           double* beta_sm, double& lamz, double& diag_add)
+{
+    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
+    if (threadIdx.x < d) {
+        const int s = j * d + threadIdx.x;
+        beta_sm[threadIdx.x] = (s == site) ? cand : th[s];
+    }
+    const int sz = d * pu + j, ss = d * pu + pu + j, so = P - 1;
+    lamz = (sz == site) ? cand : th[sz];
+    const double lamws = (ss == site) ? cand : th[ss];
+    const double lamwos = (so == site) ? cand : th[so];
+    diag_add = 1.0 / (a.lamsim[j] * lamwos) + 1.0 / lamws;
+}
+
+__global__ void __launch_bounds__(NT, 1)
+sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, int t)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Mp = round_up32(a.m);
+    EvalSmem sm = carve_eval_smem(smem_raw, Mp, a.d);
+    __shared__ double beta_sm[64];
+    const int j = blockIdx.x, c = blockIdx.y;
+    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
+    double* th = a.theta + (size_t)c * P;
+    double* sig = a.sigwl + (size_t)c * pu;
+    double* Lp = Lws + ((size_t)c * pu + j) * l_stride;
+    const double* wj = a.W + (size_t)j * a.m;
+    unsigned char* accd = a.accepted ? a.accepted + ((size_t)t * a.n_chains + c) * P : nullptr;
+
+    for (int sl = 0; sl < d + 2; ++sl) {
+        const int s = (sl < d) ? j * d + sl : (sl == d ? d * pu + j : d * pu + pu + j);
+        const size_t o = (size_t)c * P + s;
+        const int valid = pl.valid[o];
+        if (!valid) {
+            if (threadIdx.x == 0 && accd) accd[s] = 0;
+            continue;
+        }
+        const double cand = pl.cand[o];
+        double lamz, diag_add;
+        __syncthreads();
+        gather_block_params(a, th, j, s, cand, beta_sm, lamz, diag_add);
+        __syncthreads();
+        const double ll_new = eval_block_loglik(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, nullptr, nullptr);
+        if (threadIdx.x == 0) {
+            const double ll_old = sig[j];
+            const double xold = th[s];
+            const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], cand) -
+                                  elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], xold);
+            const bool acc = pl.logu[o] < ((ll_new - ll_old) + dprior) + pl.lacorr[o];
+            if (acc) {
+                th[s] = cand;
+                sig[j] = ll_new;
+            }
+            if (accd) accd[s] = acc ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+
+// mode 0: sigwl <- per-PC terms of the current state.  mode 1: sigwl_cand <- terms under candidate lamWOs.
+__global__ void __launch_bounds__(NT, 1)
+eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride,
+                double* __restrict__ sig_cand, int mode)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Mp = round_up32(a.m);
+    EvalSmem sm = carve_eval_smem(smem_raw, Mp, a.d);
+    __shared__ double beta_sm[64];
+    const int j = blockIdx.x, c = blockIdx.y;
+    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
+    const double* th = a.theta + (size_t)c * P;
+    double* Lp = Lws + ((size_t)c * pu + j) * l_stride;
+    int site = -1;
+    double cand = 0.0;
+    if (mode == 1) {
+        const size_t o = (size_t)c * P + (P - 1);
+        if (!pl.valid[o]) return;
+        site = P - 1;
+        cand = pl.cand[o];
+    }
+    double lamz, diag_add;
+    gather_block_params(a, th, j, site, cand, beta_sm, lamz, diag_add);
+    __syncthreads();
+    const double ll = eval_block_loglik(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, a.W + (size_t)j * a.m, Lp,
+                                        nullptr, nullptr);
+    if (threadIdx.x == 0) {
+        if (mode == 0) a.sigwl[(size_t)c * pu + j] = ll;
+        else sig_cand[(size_t)c * pu + j] = ll;
+    }
+}
+
+__global__ void finalize_kernel(ggp_mcmc_args a, Plan pl, const double* __restrict__ sig_cand, int t)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chains) return;
+    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
+    double* th = a.theta + (size_t)c * P;
+    double* sig = a.sigwl + (size_t)c * pu;
+    const int s = P - 1;
+    const size_t o = (size_t)c * P + s;
+    int acc = 0;
+    if (pl.valid[o]) {
+        double sn = 0.0, so = 0.0;
+        for (int j = 0; j < pu; ++j) {
+            sn += sig_cand[(size_t)c * pu + j];
+            so += sig[j];
+        }
+        const double cand = pl.cand[o];
+        const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], cand) -
+                              elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], th[s]);
+        acc = pl.logu[o] < ((sn - so) + dprior) + pl.lacorr[o];
+        if (acc) {
+            th[s] = cand;
+            for (int j = 0; j < pu; ++j) sig[j] = sig_cand[(size_t)c * pu + j];
+        }
+    }
+    if (a.accepted) a.accepted[((size_t)t * a.n_chains + c) * P + s] = (unsigned char)acc;
+    // log posterior of the state at the end of the step: sum_j SigWl[j] + block-wise prior sums
+    double ll = 0.0;
+    for (int j = 0; j < pu; ++j) ll += sig[j];
+    double lpr = 0.0;
+    const int bounds[5] = {0, d * pu, d * pu + pu, d * pu + 2 * pu, P};
+    for (int blk = 0; blk < 4; ++blk) {
+        double sblk = 0.0;
+        for (int e = bounds[blk]; e < bounds[blk + 1]; ++e)
+            sblk += elem_log_prior(a.prior_kind[e], a.prior_a[e], a.prior_b[e], th[e]);
+        lpr += sblk;
+    }
+    if (a.lp_draws) a.lp_draws[(size_t)t * a.n_chains + c] = ll + lpr;
+    if (a.draws) {
+        double* dr = a.draws + ((size_t)t * a.n_chains + c) * P;
+        for (int e = 0; e < P; ++e) dr[e] = th[e];
+    }
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace ggp
+
+using namespace ggp;
+
+extern "C" {
+
+long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains)
+{
+    if (m <= 0 || d <= 0 || pu <= 0 || n_chains <= 0) return -1;
+    const int Mp = round_up32(m);
+    const size_t P = (size_t)d * pu + 2 * pu + 1;
+    size_t b = 0;
+    b += align256((size_t)n_chains * pu * packed_doubles(Mp) * sizeof(double));   // factor workspaces
+    b += 3 * align256((size_t)n_chains * P * sizeof(double));                      // cand, lacorr, logu
+    b += align256((size_t)n_chains * P * sizeof(int));                             // valid
+    b += align256((size_t)n_chains * pu * sizeof(double));                         // sigwl_cand
+    return (long long)b;
+}
+
+int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
+{
+    GGP_ARG(args, "null args");
+    const ggp_mcmc_args a = *args;
+    GGP_ARG(a.m > 0 && a.d > 0 && a.pu > 0 && a.n_chains > 0 && a.n_steps >= 0, "sizes must be positive");
+    GGP_ARG(a.d <= 64, "d must be <= 64");
+    GGP_ARG(a.X && a.W && a.lamsim && a.theta && a.sigwl, "null model/state pointer");
+    GGP_ARG(a.prior_kind && a.prior_a && a.prior_b && a.lo && a.hi && a.prop_kind && a.fixed && a.step, "null table pointer");
+    GGP_ARG(a.workspace, "null workspace");
+    if (a.replay) GGP_ARG(a.r_cand && a.r_logacorr && a.r_logu && a.r_valid, "replay tables missing");
+    else GGP_ARG(a.uniforms && a.upos && a.n_uniform > 0, "uniform stream missing");
+    const long long need = ggp_mcmc_workspace_bytes(a.m, a.d, a.pu, a.n_chains);
+    if ((long long)a.workspace_bytes < need) {
+        set_error("ggp_mcmc_run_f64: workspace too small (%lld < %lld)", (long long)a.workspace_bytes, need);
+        return GGP_ERR_WORKSPACE;
+    }
+    if (!a.replay) {
+        const long long P = (long long)a.d * a.pu + 2 * a.pu + 1;
+        GGP_ARG(a.n_uniform >= 2 * P * a.n_steps, "uniform stream shorter than 2*P*n_steps");
+    }
+    const int Mp = round_up32(a.m);
+    const size_t smem = eval_smem_bytes(Mp, a.d);
+    if (smem > 227 * 1024) {
+        set_error("ggp_mcmc_run_f64: m=%d d=%d needs %zu B of shared memory (> 227 KB)", a.m, a.d, smem);
+        return GGP_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GGP_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    const size_t P = (size_t)a.d * a.pu + 2 * a.pu + 1;
+    unsigned char* p = reinterpret_cast<unsigned char*>(a.workspace);
+    double* Lws = reinterpret_cast<double*>(p);
+    p += align256((size_t)a.n_chains * a.pu * packed_doubles(Mp) * sizeof(double));
+    Plan pl;
+    pl.cand = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
+    pl.lacorr = reinterpret_cast<double*>(p); p += align256((size_t)a.n_chains * P * sizeof(double));
+    pl.logu = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
+    pl.valid = reinterpret_cast<int*>(p);     p += align256((size_t)a.n_chains * P * sizeof(int));
+    double* sig_cand = reinterpret_cast<double*>(p);
+    const long long l_stride = packed_doubles(Mp);
+    const dim3 grid(a.pu, a.n_chains);
+    const int cb = (a.n_chains + 31) / 32;
+
+    if (a.init_sigwl) {
+        eval_all_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, 0);
+        GGP_CUDA(cudaGetLastError());
+    }
+    for (int t = 0; t < a.n_steps; ++t) {
+        plan_kernel<<<cb, 32, 0, st>>>(a, pl, t);
+        sweep_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
+        eval_all_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, 1);
+        finalize_kernel<<<cb, 32, 0, st>>>(a, pl, sig_cand, t);
+    }
+    GGP_CUDA(cudaGetLastError());
+    return GGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+"""Thin Python wrappers over the C ABI (device tensors in, device tensors out).
+
+Each function cites the reference-side routine it stands in for; see include/gladsgp_b200.h.
+No function here has a CPU path.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import ptr, stream_ptr, check, McmcArgs
+
+
+def _f64(t, torch, dev):
+    return torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64) if not torch.is_tensor(t) else t,
+                           dtype=torch.float64, device=dev).contiguous()
+
+
+def cov_build(X, beta, lamz, diag_add):
+    """SepiaDistCov.compute_cov_mat type 1 + nugget diagonal (SURVEY A.10 cov_self).  -> (B, m, m)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = 'cuda'
+    X = _f64(X, torch, dev); beta = _f64(beta, torch, dev).reshape(-1, X.shape[1])
+    lamz = _f64(lamz, torch, dev).reshape(-1); diag_add = _f64(diag_add, torch, dev).reshape(-1)
+    B, (m, d) = beta.shape[0], X.shape
+    out = torch.empty((B, m, m), dtype=torch.float64, device=dev)
+    check(lib.ggp_cov_build_f64(ptr(X), m, d, ptr(beta), ptr(lamz), ptr(diag_add), B, ptr(out), stream_ptr()),
+          'ggp_cov_build_f64')
+    return out
+
+
+def cross_cov(X, Xp, beta, lamz):
+    """SepiaDistCov type 2 (SURVEY A.10 cov_cross).  -> (B, m, n)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = 'cuda'
+    X = _f64(X, torch, dev); Xp = _f64(Xp, torch, dev)
+    beta = _f64(beta, torch, dev).reshape(-1, X.shape[1]); lamz = _f64(lamz, torch, dev).reshape(-1)
+    B, (m, d), n = beta.shape[0], X.shape, Xp.shape[0]
+    out = torch.empty((B, m, n), dtype=torch.float64, device=dev)
+    check(lib.ggp_cross_cov_f64(ptr(X), m, ptr(Xp), n, d, ptr(beta), ptr(lamz), B, ptr(out), stream_ptr()),
+          'ggp_cross_cov_f64')
+    return out
+
+
+def loglik_batched(X, W, beta, lamz, diag_add, want_factor=False, want_u=False, factor_ws=None):
+    """doLogLik over a batch (SURVEY A.10 do_loglik).  W: (B, m).  Returns dict(loglik, info[, factor, u])."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = 'cuda'
+    X = _f64(X, torch, dev); W = _f64(W, torch, dev)
+    beta = _f64(beta, torch, dev).reshape(-1, X.shape[1])
+    lamz = _f64(lamz, torch, dev).reshape(-1); diag_add = _f64(diag_add, torch, dev).reshape(-1)
+    B, (m, d) = beta.shape[0], X.shape
+    assert W.shape == (B, m)
+    fd = lib.ggp_factor_doubles(m)
+    Mp = lib.ggp_padded_m(m)
+    if factor_ws is None:
+        factor_ws = torch.empty((B, fd), dtype=torch.float64, device=dev)
+    u = torch.empty((B, Mp), dtype=torch.float64, device=dev) if want_u else None
+    ll = torch.empty(B, dtype=torch.float64, device=dev)
+    info = torch.empty(B, dtype=torch.int32, device=dev)
+    check(lib.ggp_loglik_batched_f64(ptr(X), m, d, ptr(W), W.stride(0), ptr(beta), ptr(lamz), ptr(diag_add), B,
+                                     ptr(factor_ws), ptr(u), ptr(ll), ptr(info), stream_ptr()),
+          'ggp_loglik_batched_f64')
+    out = dict(loglik=ll, info=info)
+    if want_factor:
+        out['factor'] = factor_ws
+    if want_u:
+        out['u'] = u
+    return out
+
+
+def factor_unpack(factor_ws, m):
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    B = factor_ws.shape[0]
+    out = torch.empty((B, m, m), dtype=torch.float64, device=factor_ws.device)
+    check(lib.ggp_factor_unpack_f64(ptr(factor_ws), m, B, ptr(out), stream_ptr()), 'ggp_factor_unpack_f64')
+    return out
+
+
+PRIOR_KIND = {'Uniform': 0, 'Gamma': 1, 'Beta': 2, 'Normal': 3}
+PROP_KIND = {'Uniform': 0, 'BetaRho': 1, 'PropMH': 2}
+
+
+class McmcEngine:
+    """Owns the device-side model + tables of one sim-only SEPIA model and runs chains on it.
+
+    X (m,d) = zt, W (pu,m) PC weights, lamsim (pu,).  tables: dict of length-P numpy arrays
+    (prior_kind, prior_a, prior_b, lo, hi, prop_kind, fixed) in SEPIA sampling order.
+    """
+
+    def __init__(self, X, W, lamsim, tables, n_chains=1):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.lib = _lib.load()
+        dev = 'cuda'
+        self.X = _f64(X, torch, dev); self.W = _f64(W, torch, dev); self.lamsim = _f64(lamsim, torch, dev)
+        self.m, self.d = self.X.shape
+        self.pu = self.W.shape[0]
+        self.P = self.d * self.pu + 2 * self.pu + 1
+        self.n_chains = int(n_chains)
+        self.set_tables(tables)
+        nb = self.lib.ggp_mcmc_workspace_bytes(self.m, self.d, self.pu, self.n_chains)
+        self.ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        self.theta = torch.zeros((self.n_chains, self.P), dtype=torch.float64, device=dev)
+        self.sigwl = torch.zeros((self.n_chains, self.pu), dtype=torch.float64, device=dev)
+        self.upos = torch.zeros(self.n_chains, dtype=torch.int64, device=dev)
+        self.launches_per_step = 4
+
+    def set_tables(self, tb):
+        torch, dev = self.torch, 'cuda'
+        P = self.P
+        self.t_prior_kind = torch.as_tensor(np.asarray(tb['prior_kind'], dtype=np.int32).reshape(P), device=dev)
+        self.t_prior_a = _f64(np.asarray(tb['prior_a']).reshape(P), torch, dev)
+        self.t_prior_b = _f64(np.asarray(tb['prior_b']).reshape(P), torch, dev)
+        self.t_lo = _f64(np.asarray(tb['lo']).reshape(P), torch, dev)
+        self.t_hi = _f64(np.asarray(tb['hi']).reshape(P), torch, dev)
+        self.t_prop_kind = torch.as_tensor(np.asarray(tb['prop_kind'], dtype=np.int32).reshape(P), device=dev)
+        self.t_fixed = torch.as_tensor(np.asarray(tb['fixed'], dtype=np.uint8).reshape(P), device=dev)
+
+    def set_state(self, theta):
+        th = _f64(np.asarray(theta, dtype=np.float64).reshape(-1, self.P), self.torch, 'cuda')
+        if th.shape[0] == 1 and self.n_chains > 1:
+            th = th.expand(self.n_chains, self.P)
+        self.theta.copy_(th)
+
+    def run(self, n_steps, step, uniforms=None, replay=None, do_propMH=True, init_sigwl=True,
+            record=True, record_accept=False):
+        """step: (P,) or (n_steps,P) or (n_chains,P) [see step_axes] numpy/tensor of step sizes.
+        uniforms: (n_chains, n_uniform) U[0,1) stream, or replay = dict(cand, logacorr, logu, valid)
+        each (n_steps, n_chains, P).  Returns dict(draws, lp, accepted, consumed)."""
+        torch, dev = self.torch, 'cuda'
+        a = McmcArgs()
+        a.m, a.d, a.pu, a.n_chains, a.n_steps = self.m, self.d, self.pu, self.n_chains, int(n_steps)
+        a.do_propMH, a.init_sigwl = int(bool(do_propMH)), int(bool(init_sigwl))
+        keep = []
+        step = _f64(step, torch, dev); keep.append(step)
+        if step.dim() == 1:
+            a.step_stride_t, a.step_stride_c = 0, 0
+        elif step.shape[0] == n_steps and step.dim() == 2:
+            a.step_stride_t, a.step_stride_c = self.P, 0
+        elif step.dim() == 3:
+            a.step_stride_t, a.step_stride_c = self.n_chains * self.P, self.P
+        else:
+            raise ValueError('step must be (P,), (n_steps,P) or (n_steps,n_chains,P)')
+        a.X, a.W, a.lamsim = self.X.data_ptr(), self.W.data_ptr(), self.lamsim.data_ptr()
+        a.prior_kind, a.prior_a, a.prior_b = self.t_prior_kind.data_ptr(), self.t_prior_a.data_ptr(), self.t_prior_b.data_ptr()
+        a.lo, a.hi = self.t_lo.data_ptr(), self.t_hi.data_ptr()
+        a.prop_kind, a.fixed = self.t_prop_kind.data_ptr(), self.t_fixed.data_ptr()
+        a.step = step.data_ptr()
+        a.theta, a.sigwl = self.theta.data_ptr(), self.sigwl.data_ptr()
+        if replay is not None:
+            a.replay = 1
+            sh = (n_steps, self.n_chains, self.P)
+            rc = _f64(np.asarray(replay['cand']).reshape(sh), torch, dev)
+            ra = _f64(np.asarray(replay['logacorr']).reshape(sh), torch, dev)
+            ru = _f64(np.asarray(replay['logu']).reshape(sh), torch, dev)
+            rv = torch.as_tensor(np.asarray(replay['valid'], dtype=np.uint8).reshape(sh), device=dev)
+            keep += [rc, ra, ru, rv]
+            a.r_cand, a.r_logacorr, a.r_logu, a.r_valid = rc.data_ptr(), ra.data_ptr(), ru.data_ptr(), rv.data_ptr()
+        else:
+            a.replay = 0
+            if not torch.is_tensor(uniforms):
+                uniforms = torch.as_tensor(np.ascontiguousarray(uniforms, dtype=np.float64))
+            uniforms = uniforms.reshape(self.n_chains, -1)
+            if uniforms.device.type != 'cuda':
+                uniforms = uniforms.pin_memory().to(dev, non_blocking=True)
+            keep.append(uniforms)
+            a.uniforms, a.n_uniform = uniforms.data_ptr(), uniforms.shape[1]
+            self.upos.zero_()
+            a.upos = self.upos.data_ptr()
+        draws = lp = acc = None
+        if record:
+            draws = torch.empty((n_steps, self.n_chains, self.P), dtype=torch.float64, device=dev)
+            lp = torch.empty((n_steps, self.n_chains), dtype=torch.float64, device=dev)
+            a.draws, a.lp_draws = draws.data_ptr(), lp.data_ptr()
+        if record_accept:
+            acc = torch.empty((n_steps, self.n_chains, self.P), dtype=torch.uint8, device=dev)
+            a.accepted = acc.data_ptr()
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        check(self.lib.ggp_mcmc_run_f64(C.byref(a), stream_ptr()), 'ggp_mcmc_run_f64')
+        self._keep = keep
+        return dict(draws=draws, lp=lp, accepted=acc, consumed=self.upos)

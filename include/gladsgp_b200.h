@@ -1,0 +1,115 @@
+/* gladsgp_b200 -- C ABI of the B200-native GP-emulator hot path (libgladsgp_b200.so).
+ *
+ * The reference (timghill/GladsGP) has no FFI of its own: the path sits behind the Python package
+ * `sepia` (imports at /root/reference/src/model.py:13-15 and
+ * experiments/synthetic/analysis/assess_all_models.py:30-32).  Each entry point below names the
+ * reference-side routine it replaces; the SEPIA routines are un-vendored (requirements-cc.txt:42),
+ * so they are cited by the call site that drives them and by SURVEY.md Appendix A.
+ *
+ * Conventions: extern "C"; every function returns 0 on success or a negative GGP_ERR_* code
+ * (text via ggp_last_error_string(), thread-local); no exceptions cross the boundary; all array
+ * pointers are DEVICE pointers unless the name ends in _host; row-major; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream); the caller owns every buffer; calls are
+ * asynchronous on `stream`.
+ */
+#ifndef GLADSGP_B200_H
+#define GLADSGP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGP_VERSION 100
+
+int ggp_version(void);
+const char* ggp_last_error_string(void);
+int ggp_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* smem_optin);
+
+/* ---- (1) covariance ---------------------------------------------------------------------
+ * SepiaDistCov.compute_cov_mat type 1 (A.10 cov_self + nugget fill, as used by
+ * compute_log_lik under src/model.py:234-235):
+ *   C[b][i][j] = exp(-sum_k beta[b][k] (X[i][k]-X[j][k])^2) / lamz[b]   (i != j)
+ *   C[b][i][i] = 1/lamz[b] + diag_add[b]
+ * X[m][d], beta[B][d], lamz[B], diag_add[B], C_out[B][m][m]. */
+int ggp_cov_build_f64(const double* X, int m, int d, const double* beta, const double* lamz,
+                      const double* diag_add, int B, double* C_out, void* stream);
+
+/* SepiaDistCov type 2 (cross covariance; SURVEY A.10 cov_cross, used by wPred under
+ * assess_all_models.py:489-490):  S21[b][i][t] = exp(-sum_k beta[b][k](X[i][k]-Xp[t][k])^2)/lamz[b]
+ * X[m][d], Xp[n][d], S21_out[B][m][n]. */
+int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, const double* beta,
+                      const double* lamz, int B, double* S21_out, void* stream);
+
+/* ---- (2) fused covariance + Cholesky + log-determinant + forward solve ------------------------
+ * doLogLik / compute_log_lik (A.10 do_loglik): for each b
+ *   loglik[b] = -sum_i log L_ii - 0.5 ||L^-1 W[b]||^2 ,  L = chol(C[b]) (C as above, never stored)
+ * info[b] = 0, or the 1-based index of the first non-positive pivot (then loglik[b] = -inf; the
+ * reference maps a failed Cholesky to -inf the same way).
+ * W: vector b starts at W + b*w_stride.  factor_ws[B][ggp_factor_doubles(m)] receives the packed
+ * factor (layout in DESIGN.md; unpack with ggp_factor_unpack_f64).  u_out (nullable)
+ * [B][ggp_padded_m(m)] receives L^-1 W[b], zero padded.  info_out nullable. */
+long long ggp_factor_doubles(int m);
+int ggp_padded_m(int m);
+int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long long w_stride,
+                           const double* beta, const double* lamz, const double* diag_add, int B,
+                           double* factor_ws, double* u_out, double* loglik_out, int* info_out, void* stream);
+int ggp_factor_unpack_f64(const double* factor_ws, int m, int B, double* L_dense, void* stream);
+
+/* ---- Metropolis-within-Gibbs sampler ------------------------------------------------------------
+ * SepiaModel.mcmc_step / do_mcmc (A.4-A.6, A.10 mcmc_step), n_chains independent
+ * chains of one model.  Parameter vector theta[P], P = d*pu + 2*pu + 1, in SEPIA's sampling order:
+ * betaU in Fortran order (all d inputs of PC 0, then PC 1, ...), lamUz[pu], lamWs[pu], lamWOs.
+ * Per-element tables have length P.  Enumerations:
+ *   prior_kind: 0 Uniform, 1 Gamma(a, b = rate), 2 Beta(a, b) on rho = exp(-x/4) (rho clamped to
+ *               0.999), 3 Normal(a = mean, b = sd)
+ *   prop_kind : 0 Uniform  x + step*U(-.5,.5);  1 BetaRho;  2 PropMH (Uniform when !do_propMH)
+ * Two ways to feed randomness:
+ *   replay = 0: uniforms[n_chains][n_uniform] is a pre-drawn U[0,1) stream per chain, consumed
+ *               exactly like SEPIA consumes np.random (one draw per visited site, one more iff the
+ *               candidate is in bounds and aCorr > 0); upos[n_chains] (in/out) = draws consumed.
+ *   replay = 1: r_cand / r_logacorr / r_logu / r_valid [n_steps][n_chains][P] give every
+ *               candidate, log(aCorr), log(u) and validity explicitly (bit-exact replays).
+ * step: element s of chain c at step t is step[t*step_stride_t + c*step_stride_c + s].
+ * Outputs (nullable): draws[n_steps][n_chains][P], lp_draws[n_steps][n_chains],
+ * accepted[n_steps][n_chains][P].  theta and sigwl[n_chains][pu] are updated in place;
+ * init_sigwl != 0 recomputes sigwl from theta first. */
+typedef struct ggp_mcmc_args {
+    int m, d, pu, n_chains, n_steps;
+    int do_propMH, replay, init_sigwl;
+    const double* X;       /* [m][d]   zt = [dummy x | t]           */
+    const double* W;       /* [pu][m]  PC weights                   */
+    const double* lamsim;  /* [pu]     diag(K K^T)                  */
+    const int* prior_kind;
+    const double* prior_a;
+    const double* prior_b;
+    const double* lo;
+    const double* hi;
+    const int* prop_kind;
+    const unsigned char* fixed;
+    const double* step;
+    long long step_stride_t, step_stride_c;
+    double* theta;         /* [n_chains][P] in/out */
+    double* sigwl;         /* [n_chains][pu] in/out */
+    const double* uniforms;
+    long long n_uniform;
+    long long* upos;
+    const double* r_cand;
+    const double* r_logacorr;
+    const double* r_logu;
+    const unsigned char* r_valid;
+    double* draws;
+    double* lp_draws;
+    unsigned char* accepted;
+    void* workspace;
+    size_t workspace_bytes;
+} ggp_mcmc_args;
+
+long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains);
+int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLADSGP_B200_H */

@@ -1,0 +1,132 @@
+"""GPU parity: covariance build, fused log-likelihood, MCMC replay vs the CPU oracle (through the C ABI)."""
+import numpy as np
+import pytest
+
+from helpers import so, make_problem, make_scalar_problem, random_hypers, tables_from_oracle, replay_from_trace
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-8        # north_star: log-likelihoods within 1e-8 relative in FP64
+
+
+def _oracle_ll(num, beta, lamz, lamws, lamwos, j):
+    C = so.block_cov(num, beta, lamz, lamws, lamwos, j)
+    return C, so.do_loglik(C, num.wv[j * num.m:(j + 1) * num.m, 0])
+
+
+@pytest.mark.parametrize('m,q,pu', [(33, 2, 1), (64, 3, 2), (100, 8, 5), (257, 4, 2), (512, 8, 3)])
+def test_cov_and_loglik_match_oracle(cuda, m, q, pu):
+    from gladsgp_b200 import ops
+    pr = make_problem(m=m, q=q, pu=pu)
+    num = pr['num']
+    B = 2 * pu
+    beta, lamz, lamws, lamwos = random_hypers(num, B, seed=m)
+    js = np.arange(B) % pu
+    dadd = 1.0 / (num.LamSim[js] * lamwos) + 1.0 / lamws
+    W = np.stack([num.wv[j * m:(j + 1) * m, 0] for j in js])
+    Cg = ops.cov_build(num.zt, beta, lamz, dadd).cpu().numpy()
+    out = ops.loglik_batched(num.zt, W, beta, lamz, dadd, want_factor=True, want_u=True)
+    ll = out['loglik'].cpu().numpy()
+    Lg = ops.factor_unpack(out['factor'], m).cpu().numpy()
+    ug = out['u'].cpu().numpy()[:, :m]
+    assert np.all(out['info'].cpu().numpy() == 0)
+    for b in range(B):
+        C, ref = _oracle_ll(num, beta[b], lamz[b], lamws[b], lamwos[b], js[b])
+        np.testing.assert_allclose(Cg[b], C, rtol=1e-13, atol=1e-300)
+        assert abs(ll[b] - ref) <= LL_RTOL * abs(ref), (b, ll[b], ref)
+        L = np.linalg.cholesky(C)
+        np.testing.assert_allclose(Lg[b], L, rtol=0, atol=1e-9 * np.abs(L).max())
+        u = np.linalg.solve(L, W[b])
+        np.testing.assert_allclose(ug[b], u, rtol=0, atol=1e-8 * np.abs(u).max())
+
+
+def test_loglik_scalar_1d_m1000(cuda):
+    """cfg 2 shape: m=1000, d=2, pu=1 (multi-pass panels)."""
+    from gladsgp_b200 import ops
+    pr = make_scalar_problem(m=1000)
+    num = pr['num']
+    beta = np.array([[0.1, 30.0], [0.5, 80.0]]); lamz = np.array([0.8, 1.3])
+    dadd = 1.0 / (1.0 * np.array([150.0, 90.0])) + 1.0 / np.array([800.0, 2000.0])
+    W = np.stack([num.wv[:, 0]] * 2)
+    ll = ops.loglik_batched(num.zt, W, beta, lamz, dadd)['loglik'].cpu().numpy()
+    for b in range(2):
+        C = so.cov_self(num, beta[b], lamz[b]); np.fill_diagonal(C, C.diagonal() + dadd[b])
+        ref = so.do_loglik(C, num.wv[:, 0])
+        assert abs(ll[b] - ref) <= LL_RTOL * abs(ref), (ll[b], ref)
+
+
+def test_loglik_not_positive_definite_is_minus_inf(cuda):
+    from gladsgp_b200 import ops
+    pr = make_problem(m=64, q=3, pu=2)
+    num = pr['num']
+    beta = np.full((1, num.d), 1e-6); lamz = np.array([1.0]); dadd = np.array([-0.999999])
+    out = ops.loglik_batched(num.zt, num.wv[:64, 0][None, :], beta, lamz, dadd)
+    assert out['loglik'].cpu().numpy()[0] == -np.inf
+    assert out['info'].cpu().numpy()[0] > 0
+
+
+def test_cross_cov_matches_oracle(cuda):
+    from gladsgp_b200 import ops
+    pr = make_problem(m=100, q=8, pu=2)
+    num = pr['num']
+    rng = np.random.default_rng(1)
+    xp = np.concatenate([0.5 * np.ones((37, 1)), rng.uniform(size=(37, 8))], axis=1)
+    beta, lamz, _, _ = random_hypers(num, 3, seed=9)
+    S = ops.cross_cov(num.zt, xp, beta, lamz).cpu().numpy()
+    for b in range(3):
+        np.testing.assert_allclose(S[b], so.cov_cross(num.zt, xp, beta[b], lamz[b]), rtol=1e-13)
+
+
+@pytest.mark.parametrize('override', [False, True])
+def test_mcmc_replay_matches_oracle_chain(cuda, override):
+    """Chains identical given the same proposals and uniforms (north_star)."""
+    from gladsgp_b200 import ops
+    pr = make_problem(m=64, q=3, pu=2)
+    num = pr['num']
+    mod = so.OracleModel(num)
+    if override:
+        mod.override_lamWOs(50.0)
+    tb = tables_from_oracle(mod)
+    P = tb['theta'].size
+    n_steps = 12
+    rng = np.random.RandomState(11)
+    mod.trace = []
+    mod.do_mcmc(n_steps, rng=rng)
+    replay, acc_ref = replay_from_trace(mod.trace, n_steps, P)
+    ref = mod.get_samples()
+    ref_draws = np.concatenate([ref['betaU'], ref['lamUz'], ref['lamWs'], ref['lamWOs']], axis=1)
+    eng = ops.McmcEngine(num.zt, num.w.T.copy(), num.LamSim, tb, n_chains=1)
+    eng.set_state(tb['theta'])
+    out = eng.run(n_steps, tb['step'], replay=replay, record_accept=True)
+    acc = out['accepted'].cpu().numpy()
+    draws = out['draws'].cpu().numpy()[:, 0, :]
+    lp = out['lp'].cpu().numpy()[:, 0]
+    assert np.array_equal(acc, acc_ref)
+    assert np.array_equal(draws, ref_draws)            # bit-identical chain under replay
+    np.testing.assert_allclose(lp, ref['logPost'][:, 0], rtol=1e-9)
+
+
+def test_mcmc_uniform_stream_matches_oracle(cuda):
+    """Device-side proposal generation from the same U[0,1) stream as np.random."""
+    from gladsgp_b200 import ops
+    pr = make_problem(m=64, q=3, pu=2)
+    num = pr['num']
+    mod = so.OracleModel(num)
+    tb = tables_from_oracle(mod)
+    P = tb['theta'].size
+    n_steps = 10
+    rs = np.random.RandomState(123)
+    stream = rs.random_sample(2 * P * n_steps)
+    rs = np.random.RandomState(123)
+    mod.trace = []
+    mod.do_mcmc(n_steps, rng=rs)
+    used = sum(1 + int(tr['valid']) for tr in mod.trace)
+    ref = mod.get_samples()
+    ref_draws = np.concatenate([ref['betaU'], ref['lamUz'], ref['lamWs'], ref['lamWOs']], axis=1)
+    eng = ops.McmcEngine(num.zt, num.w.T.copy(), num.LamSim, tb, n_chains=1)
+    eng.set_state(tb['theta'])
+    out = eng.run(n_steps, tb['step'], uniforms=stream[None, :], record_accept=True)
+    assert int(out['consumed'].cpu().numpy()[0]) == used
+    acc_ref = np.array([tr['accept'] for tr in mod.trace], dtype=np.uint8).reshape(n_steps, 1, P)
+    assert np.array_equal(out['accepted'].cpu().numpy(), acc_ref)
+    np.testing.assert_allclose(out['draws'].cpu().numpy()[:, 0, :], ref_draws, rtol=1e-12)
