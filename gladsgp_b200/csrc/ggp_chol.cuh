@@ -50,6 +50,53 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     return s;
 }
 
+// S += A[rows, 0:32j] * Lb[panel rows, 0:32j]^T for NU 8-row units of one warp (DMMA.8x8x4).
+// A-operand rows come from `Ap` (packed factor layout when a_ld == 0, else a [slab][a_ld][8] layout
+// indexed by local row), B-operand rows from the packed factor `Lb`.  NU is a template parameter so
+// that no predicated-off DMMA is ever issued (a predicated-off DMMA still occupies the pipe).
+template <int NU>
+static __device__ __forceinline__ void panel_gemm(double (&acc)[4][4][2], const double* __restrict__ Ap,
+                                                  const double* __restrict__ Lb, int Mp, int j, int row0,
+                                                  const int (&rb)[4], int g, int q, int a_ld)
+{
+    const int nsl = 4 * j;
+    auto a_slab = [&](int s) -> const double* {
+        if (a_ld) return Ap + (size_t)s * a_ld * 8;
+        int kb = s >> 2, ks = s & 3;
+        return Ap + panel_off(kb, Mp) + (long long)ks * (Mp - 32 * kb) * 8 - 32LL * kb * 8;
+    };
+    auto b_slab = [&](int s) -> const double* {
+        int kb = s >> 2, ks = s & 3;
+        return Lb + panel_off(kb, Mp) + (long long)ks * (Mp - 32 * kb) * 8 - 32LL * kb * 8;
+    };
+    double2 an[NU];
+    {
+        const double* sl = a_slab(0);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) an[i] = ldcg2(sl + (rb[i] + g) * 8 + 2 * q);
+    }
+    for (int s = 0; s < nsl; ++s) {
+        const double* sl = b_slab(s);
+        double2 a[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) a[i] = an[i];
+        if (s + 1 < nsl) {
+            const double* sn = a_slab(s + 1);
+#pragma unroll
+            for (int i = 0; i < NU; ++i) an[i] = ldcg2(sn + (rb[i] + g) * 8 + 2 * q);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const double2 b = *reinterpret_cast<const double2*>(sl + (row0 + 8 * cb + g) * 8 + 2 * q);
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b.x);
+                dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b.y);
+            }
+        }
+    }
+}
+
 // Whole-CTA evaluation (NT threads).  Returns the block log-likelihood term to every thread;
 // *info (if non-null, written by thread 0) = 0 or 1-based index of the failing pivot.
 // beta may point to global or shared memory.  Lp is the packed-factor workspace (packed_doubles(Mp)).
@@ -104,39 +151,12 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
             }
 
             if (act[0] && j > 0) {
-                const int nsl = 4 * j;
-                // slab s = (kb, ks); pointer such that slab[r*8 + c] addresses global row r
-                auto slab_ptr = [&](int s) -> const double* {
-                    int kb = s >> 2, ks = s & 3;
-                    return Lp + panel_off(kb, Mp) + (long long)ks * (Mp - 32 * kb) * 8 - 32LL * kb * 8;
-                };
-                double2 an[4];
-                {
-                    const double* sl = slab_ptr(0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) an[i] = ldcg2(sl + (rb[i] + g) * 8 + 2 * q);
-                }
-                for (int s = 0; s < nsl; ++s) {
-                    const double* sl = slab_ptr(s);
-                    double2 a[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = an[i];
-                    if (s + 1 < nsl) {
-                        const double* sn = slab_ptr(s + 1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) an[i] = ldcg2(sn + (rb[i] + g) * 8 + 2 * q);
-                    }
-#pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) {
-                        const double2 b = *reinterpret_cast<const double2*>(sl + (row0 + 8 * cb + g) * 8 + 2 * q);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (act[i]) {
-                                dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b.x);
-                                dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b.y);
-                            }
-                        }
-                    }
+                const int nmine = (nun - warp + NWARP - 1) / NWARP;     // units owned by this warp (1..4)
+                switch (nmine) {
+                    case 1: panel_gemm<1>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
+                    case 2: panel_gemm<2>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
+                    case 3: panel_gemm<3>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
+                    default: panel_gemm<4>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
                 }
             }
 

@@ -183,3 +183,98 @@ class McmcEngine:
         check(self.lib.ggp_mcmc_run_f64(C.byref(a), stream_ptr()), 'ggp_mcmc_run_f64')
         self._keep = keep
         return dict(draws=draws, lp=lp, accepted=acc, consumed=self.upos)
+
+
+class Predictor:
+    """Cached-factor predictor for a set of B = nsamp*pu (sample, PC) hyper-parameter blocks.
+
+    Factors every S22 once (the reference re-solves it for every call), then pushes
+    blocks of test designs through ggp_predict_f64.
+    """
+
+    def __init__(self, X, W, beta, lamz, diag_add, s11_diag):
+        torch = _lib.require_cuda()
+        self.torch, self.lib = torch, _lib.load()
+        dev = 'cuda'
+        self.X = _f64(X, torch, dev)
+        self.m, self.d = self.X.shape
+        self.beta = _f64(beta, torch, dev).reshape(-1, self.d)
+        self.B = self.beta.shape[0]
+        self.lamz = _f64(lamz, torch, dev).reshape(-1)
+        self.s11 = _f64(s11_diag, torch, dev).reshape(-1)
+        out = loglik_batched(self.X, W, self.beta, self.lamz, diag_add, want_factor=True, want_u=True)
+        self.factor, self.u, self.loglik, self.info = out['factor'], out['u'], out['loglik'], out['info']
+        self.Mp = self.u.shape[1]
+        self._ws = None
+
+    def predict(self, Xp, want_V=False):
+        """Xp (n,d) -> mean (B,n), var (B,n)[, V (B,n,Mp)]."""
+        torch, lib, dev = self.torch, self.lib, 'cuda'
+        Xp = _f64(Xp, torch, dev)
+        n = Xp.shape[0]
+        need = lib.ggp_predict_workspace_bytes(self.m, n, self.B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        mean = torch.empty((self.B, n), dtype=torch.float64, device=dev)
+        var = torch.empty((self.B, n), dtype=torch.float64, device=dev)
+        V = torch.empty((self.B, n, self.Mp), dtype=torch.float64, device=dev) if want_V else None
+        check(lib.ggp_predict_f64(ptr(self.X), self.m, self.d, ptr(self.factor), ptr(self.u), ptr(self.beta),
+                                  ptr(self.lamz), ptr(self.s11), ptr(Xp), n, self.B, ptr(mean), ptr(var), ptr(V),
+                                  ptr(self._ws), self._ws.numel(), stream_ptr()), 'ggp_predict_f64')
+        return (mean, var, V) if want_V else (mean, var)
+
+    def pred_cov(self, Xp, V):
+        """Joint covariance Sigma (B,n,n) = S11 - V V^T."""
+        torch, lib, dev = self.torch, self.lib, 'cuda'
+        Xp = _f64(Xp, torch, dev)
+        n = Xp.shape[0]
+        Sig = torch.empty((self.B, n, n), dtype=torch.float64, device=dev)
+        check(lib.ggp_pred_cov_f64(ptr(Xp), n, self.d, ptr(self.beta), ptr(self.lamz), ptr(self.s11), ptr(V),
+                                   self.m, self.B, ptr(Sig), stream_ptr()), 'ggp_pred_cov_f64')
+        return Sig
+
+
+def reconstruct(w, K, sd, mean, out=None):
+    """get_y: w (R,pu) f32, K (pu,n_y) f32, sd/mean scalar or (n_y,) -> y (R,n_y) f32 on the device."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = 'cuda'
+
+    def f32(t):
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.ascontiguousarray(np.asarray(t, dtype=np.float32)))
+        return t.to(device=dev, dtype=torch.float32).contiguous()
+    w = f32(w); K = f32(K); sd = f32(sd).reshape(-1); mean = f32(mean).reshape(-1)
+    R, pu = w.shape
+    n_y = K.shape[1]
+    if out is None:
+        out = torch.empty((R, n_y), dtype=torch.float32, device=dev)
+    check(lib.ggp_reconstruct_f32(ptr(w), ptr(K), ptr(sd), sd.numel(), ptr(mean), mean.numel(), R, pu, n_y,
+                                  ptr(out), stream_ptr()), 'ggp_reconstruct_f32')
+    return out
+
+
+def rsvd_sketch(X, omegaT, ws=None):
+    """Y = X @ omega  (src/svd.py:52), omegaT = omega.T (r,n) f32 device tensor."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    m, n = X.shape
+    r = omegaT.shape[0]
+    need = lib.ggp_rsvd_workspace_bytes(m)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device='cuda')
+    Y = torch.empty((m, r), dtype=torch.float32, device='cuda')
+    check(lib.ggp_rsvd_sketch_f32(ptr(X), m, n, ptr(omegaT), r, ptr(Y), ptr(ws), ws.numel(), stream_ptr()),
+          'ggp_rsvd_sketch_f32')
+    return Y
+
+
+def rsvd_xty(X, Y):
+    """Bt (r,n) = Y^T X  (src/svd.py:60 with Y = Q)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    m, n = X.shape
+    r = Y.shape[1]
+    Bt = torch.empty((r, n), dtype=torch.float32, device='cuda')
+    check(lib.ggp_rsvd_xty_f32(ptr(X), m, n, ptr(Y.contiguous()), r, ptr(Bt), stream_ptr()), 'ggp_rsvd_xty_f32')
+    return Bt

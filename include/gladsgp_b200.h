@@ -109,6 +109,42 @@ typedef struct ggp_mcmc_args {
 long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains);
 int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream);
 
+/* ---- (3) posterior prediction ------------------------------------------------------------------
+ * SepiaPredict.wPred (A.7, A.10 w_pred; callers assess_all_models.py:489-490,
+ * plot_test_error.py:77, time_predictions.py:76).  For every (posterior sample, PC) pair b the
+ * caller first factors S22 once with ggp_loglik_batched_f64 (factor + u = L^-1 w); then
+ *   V[b]      = S21[b]^T L[b]^-T                         (n x m, rows = test designs)
+ *   mean[b]   = V[b] u[b]                                = S21^T S22^-1 w
+ *   var[b][t] = s11_diag[b] - sum_k V[b][t][k]^2         = diag(S11 - S21^T S22^-1 S21)
+ * factor[B][ggp_factor_doubles(m)], u[B][ggp_padded_m(m)], beta[B][d], lamz[B], s11_diag[B]
+ * (= 1/lamUz + 1/lamWs), Xp[n][d].  V_out nullable: [B][n][ggp_padded_m(m)].
+ * workspace: ggp_predict_workspace_bytes(m, n, B). */
+long long ggp_predict_workspace_bytes(int m, int n, int B);
+int ggp_predict_f64(const double* X, int m, int d, const double* factor, const double* u, const double* beta,
+                    const double* lamz, const double* s11_diag, const double* Xp, int n, int B,
+                    double* mean_out, double* var_out, double* V_out, void* workspace, long long workspace_bytes,
+                    void* stream);
+/* Joint predictive covariance of n designs (the per-PC block of SEPIA's Syhat):
+ *   Sigma[b] = S11[b] - V[b] V[b]^T,  S11 off-diagonal = cov(xp_s, xp_t), diagonal = s11_diag[b]. */
+int ggp_pred_cov_f64(const double* Xp, int n, int d, const double* beta, const double* lamz,
+                     const double* s11_diag, const double* V, int m, int B, double* Sigma_out, void* stream);
+
+/* SepiaEmulatorPrediction.get_y (assess_all_models.py:492), float32:
+ *   y[r][c] = (sum_p w[r][p] K[p][c]) * sd[c] + mean[c],  r < R (= nsamp*npred), c < n_y.
+ * sd_len / mean_len are 1 (scalar) or n_y. */
+int ggp_reconstruct_f32(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
+                        int mean_len, int R, int pu, long long n_y, float* y_out, void* stream);
+
+/* ---- (4) randomized SVD passes -----------------------------------------------------------------
+ * src/svd.py:52  Y = X @ omega           -> ggp_rsvd_sketch_f32 (OmegaT = omega^T, [r][n])
+ * src/svd.py:56  Y = X @ X.T @ Y         -> ggp_rsvd_xty_f32 then ggp_rsvd_sketch_f32 (X (X^T Y))
+ * src/svd.py:60  B = Q.T @ X             -> ggp_rsvd_xty_f32 (Bt_out[r][n] = Y^T X)
+ * X[m][n] float32 row-major.  workspace: ggp_rsvd_workspace_bytes(m). */
+long long ggp_rsvd_workspace_bytes(int m);
+int ggp_rsvd_sketch_f32(const float* X, int m, long long n, const float* OmegaT, int r, float* Y_out,
+                        void* workspace, long long workspace_bytes, void* stream);
+int ggp_rsvd_xty_f32(const float* X, int m, long long n, const float* Y, int r, float* Bt_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

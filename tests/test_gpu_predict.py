@@ -1,0 +1,101 @@
+"""GPU parity: prediction moments, reconstruction and rSVD passes vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import so, svd_oracle, synthetic, make_problem, make_scalar_problem
+
+pytestmark = pytest.mark.gpu
+
+PRED_RTOL = 1e-6      # north_star: predictive means and variances within 1e-6 relative
+
+
+def _blocks(num, samples):
+    """(sample, PC) hyper-parameter blocks in (s, j) order, as float64."""
+    d, pu, m = num.d, num.pu, num.m
+    ns = samples['lamWs'].shape[0]
+    beta = np.zeros((ns * pu, d)); lamz = np.zeros(ns * pu); dadd = np.zeros(ns * pu); s11 = np.zeros(ns * pu)
+    W = np.zeros((ns * pu, m))
+    for s in range(ns):
+        bU = np.asarray(samples['betaU'][s], dtype=np.float64).reshape((d, pu), order='F')
+        for j in range(pu):
+            b = s * pu + j
+            lz = float(samples['lamUz'][s, j]); lw = float(samples['lamWs'][s, j]); lo = float(samples['lamWOs'][s, 0])
+            beta[b] = bU[:, j]; lamz[b] = lz
+            dadd[b] = 1.0 / (num.LamSim[j] * lo) + 1.0 / lw
+            s11[b] = 1.0 / lz + 1.0 / lw
+            W[b] = num.wv[j * m:(j + 1) * m, 0]
+    return beta, lamz, dadd, s11, W
+
+
+@pytest.mark.parametrize('m,q,pu,npred', [(64, 3, 2, 5), (100, 8, 5, 4), (257, 4, 2, 37)])
+def test_predict_moments_match_oracle(cuda, m, q, pu, npred):
+    from gladsgp_b200 import ops
+    pr = make_problem(m=m, q=q, pu=pu)
+    num = pr['num']
+    samples = synthetic.posterior_samples(6, num.d, pu, seed=m)
+    tp = synthetic.test_design(npred, q)
+    _, mu, Sig = so.w_pred(num, tp, samples, draw=False)
+    beta, lamz, dadd, s11, W = _blocks(num, samples)
+    P = ops.Predictor(num.zt, W, beta, lamz, dadd, s11)
+    xp = np.concatenate([0.5 * np.ones((npred, 1)), tp.astype(np.float64)], axis=1)
+    mean, var, V = P.predict(xp, want_V=True)
+    Sg = P.pred_cov(xp, V).cpu().numpy()
+    mean = mean.cpu().numpy(); var = var.cpu().numpy()
+    scale = np.abs(mu).max()
+    for s in range(6):
+        for j in range(pu):
+            b = s * pu + j
+            sl = slice(j * npred, (j + 1) * npred)
+            np.testing.assert_allclose(mean[b], mu[s, sl], rtol=PRED_RTOL, atol=PRED_RTOL * scale)
+            np.testing.assert_allclose(var[b], np.diag(Sig[s, sl, sl]), rtol=PRED_RTOL)
+            np.testing.assert_allclose(Sg[b], Sig[s, sl, sl], rtol=PRED_RTOL, atol=PRED_RTOL * np.abs(Sig[s, sl, sl]).max())
+
+
+def test_predict_many_designs_blocks(cuda):
+    """More designs than one 512-row task; moments must not depend on the blocking."""
+    from gladsgp_b200 import ops
+    pr = make_problem(m=64, q=3, pu=2)
+    num = pr['num']
+    samples = synthetic.posterior_samples(3, num.d, 2, seed=1)
+    tp = synthetic.test_design(1100, 3)
+    xp = np.concatenate([0.5 * np.ones((1100, 1)), tp.astype(np.float64)], axis=1)
+    beta, lamz, dadd, s11, W = _blocks(num, samples)
+    P = ops.Predictor(num.zt, W, beta, lamz, dadd, s11)
+    mean, var = P.predict(xp)
+    m2, v2 = P.predict(xp[500:600])
+    assert np.array_equal(mean.cpu().numpy()[:, 500:600], m2.cpu().numpy())
+    assert np.array_equal(var.cpu().numpy()[:, 500:600], v2.cpu().numpy())
+    _, mu, Sig = so.w_pred(num, tp[:8], samples, draw=False)
+    np.testing.assert_allclose(mean.cpu().numpy()[0, :8], mu[0, :8], rtol=PRED_RTOL, atol=1e-6 * np.abs(mu).max())
+
+
+@pytest.mark.parametrize('n_y', [1000, 4099])
+def test_reconstruct_matches_get_y(cuda, n_y):
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(0)
+    R, pu = 37, 10
+    w = rng.standard_normal((R, pu)).astype(np.float32)
+    K = rng.standard_normal((pu, n_y)).astype(np.float32)
+    sd = rng.uniform(0.1, 2.0, n_y).astype(np.float32); mu = rng.standard_normal(n_y).astype(np.float32)
+    ref = so.get_y(w[None], K, sd, mu)[0]
+    y = ops.reconstruct(w, K, sd, mu).cpu().numpy()
+    np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-5)
+    y1 = ops.reconstruct(w, K, np.float32(1.7), np.float32(0.3)).cpu().numpy()
+    np.testing.assert_allclose(y1, so.get_y(w[None], K, np.float32(1.7), np.float32(0.3))[0], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('m,n,r', [(64, 1000, 25), (100, 5003, 25), (128, 3000, 40)])
+def test_rsvd_passes_match_numpy(cuda, m, n, r):
+    from gladsgp_b200 import ops
+    torch = cuda
+    rng = np.random.default_rng(m)
+    X = rng.standard_normal((m, n)).astype(np.float32)
+    om = rng.standard_normal((n, r)).astype(np.float32)
+    Xd = torch.as_tensor(X, device='cuda')
+    Y = ops.rsvd_sketch(Xd, torch.as_tensor(om.T.copy(), device='cuda')).cpu().numpy()
+    ref = X.astype(np.float64) @ om.astype(np.float64)
+    np.testing.assert_allclose(Y, ref, rtol=0, atol=3e-5 * np.abs(ref).max())
+    Yq = rng.standard_normal((m, r)).astype(np.float32)
+    Bt = ops.rsvd_xty(Xd, torch.as_tensor(Yq, device='cuda')).cpu().numpy()
+    refB = Yq.astype(np.float64).T @ X.astype(np.float64)
+    np.testing.assert_allclose(Bt, refB, rtol=0, atol=3e-5 * np.abs(refB).max())
