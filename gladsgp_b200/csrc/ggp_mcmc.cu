@@ -56,6 +56,10 @@ __global__ void plan_kernel(ggp_mcmc_args a, Plan pl, int t)
         const size_t o = (size_t)c * P + s;
         double cand, lac = 0.0, lu = 0.0;
         int valid;
+        if (a.fixed[s] == 2) {            // block not in mcmcList: never visited, consumes no randomness
+            pl.cand[o] = th[s]; pl.lacorr[o] = 0.0; pl.logu[o] = 0.0; pl.valid[o] = 0;
+            continue;
+        }
         if (a.replay) {
             const size_t ro = ((size_t)t * a.n_chains + c) * P + s;
             cand = a.r_cand[ro];

@@ -1,0 +1,174 @@
+"""SepiaEmulatorPrediction mirror (8b).
+
+Callers (always t_pred= / samples= / model= keywords):
+/root/reference/experiments/synthetic/analysis/assess_all_models.py:489-492,510-513;
+plot_test_error.py:77-80; time_predictions.py:76-79; sensitivity_indices.py:85-88;
+fit_scalar_models.py:481-483; include_trunc_error.py:86-88.
+
+Differences from the reference implementation, all behind the same results:
+* every (sample, PC) covariance is factored ONCE per prediction object (SEPIA re-solves S22 for
+  every call) and test designs are pushed through the cached factor on the GPU;
+* the multivariate-normal realisation uses an eigen-factor of each per-PC covariance block instead of
+  one SVD of the block-diagonal matrix: same distribution, and the same np.random.normal draws are
+  consumed, but a realisation is not bit-comparable with SEPIA's (SVD sign ambiguity);
+  parity is asserted on mu / Sigma (storeMuSigma=True).
+"""
+import numpy as np
+
+from .. import ops, _lib
+
+MAX_JOINT = 1024      # above this many designs per call the joint covariance is not formed
+
+
+class SepiaPrediction:
+    def __init__(self, x_pred=None, samples=None, model=None, t_pred=None, addResidVar=False,
+                 storeRlz=True, storeMuSigma=False):
+        if samples is None or model is None:
+            raise TypeError('samples and model are required')
+        if x_pred is None and t_pred is None:
+            raise TypeError('at least one of x_pred, t_pred is required')
+        data = model.data
+        sd = data.sim_data
+        if t_pred is not None:
+            t_pred = np.asarray(t_pred)
+            if t_pred.ndim == 1:
+                t_pred = t_pred[None, :]
+        npred = (t_pred if t_pred is not None else np.asarray(x_pred)).shape[0]
+        if x_pred is None:
+            if not data.dummy_x:
+                raise TypeError('x_pred is required for a model built with x_sim')
+            x_pred = 0.5 * np.ones((npred, 1))
+        x_pred = np.asarray(x_pred)
+        if x_pred.ndim == 1:
+            x_pred = x_pred[:, None]
+        if x_pred.shape[1] != model.num.p or (t_pred is not None and t_pred.shape[1] != model.num.q):
+            raise ValueError('x_pred / t_pred have the wrong number of columns')
+        if (t_pred is None) != (model.num.q == 0):
+            raise ValueError('t_pred must be given iff the model has t inputs')
+        self.model = model
+        self.xpred, self.t_pred = x_pred, t_pred
+        xt, tt = data.transform_xt(x=x_pred, t=t_pred)
+        if data.dummy_x:
+            xt = 0.5 * np.ones((npred, 1))
+        cols = [np.asarray(xt, dtype=np.float64)]
+        if tt is not None:
+            cols.append(np.asarray(tt, dtype=np.float64))
+        self.xpredt = np.ascontiguousarray(np.concatenate(cols, axis=1))
+        self.samples = samples
+        self.addResidVar = addResidVar
+        self.storeRlz = storeRlz
+        self.storeMuSigma = storeMuSigma
+        self.w = None
+        self.mu = None
+        self.sigma = None
+
+
+class SepiaEmulatorPrediction(SepiaPrediction):
+    def __init__(self, x_pred=None, samples=None, model=None, t_pred=None, addResidVar=False,
+                 storeRlz=True, storeMuSigma=False, do_call=True, joint=None):
+        super().__init__(x_pred=x_pred, samples=samples, model=model, t_pred=t_pred, addResidVar=addResidVar,
+                         storeRlz=storeRlz, storeMuSigma=storeMuSigma)
+        self.joint = joint
+        if do_call:
+            self._w_pred()
+
+    # ------------------------------------------------------------------ wPred
+    def _blocks(self):
+        num = self.model.num
+        d, pu, m = num.p + num.q, num.pu, num.m
+        s = self.samples
+        lamUz = np.asarray(s['lamUz'], dtype=np.float64).reshape(-1, pu)
+        lamWs = np.asarray(s['lamWs'], dtype=np.float64).reshape(-1, pu)
+        lamWOs = np.asarray(s['lamWOs'], dtype=np.float64).reshape(-1, 1)
+        ns = lamUz.shape[0]
+        bU = np.asarray(s['betaU'], dtype=np.float64).reshape(ns, -1)
+        if bU.shape[1] != d * pu:
+            raise ValueError('samples["betaU"] must be flat (n, %d); got %s' % (d * pu, np.asarray(s['betaU']).shape))
+        beta = bU.reshape(ns, pu, d).reshape(ns * pu, d)          # row (s, j) = betaU[:, j] (Fortran flat)
+        lamz = lamUz.reshape(-1)
+        dadd = (1.0 / (num.LamSim[None, :] * lamWOs) + 1.0 / lamWs).reshape(-1)
+        s11 = (1.0 / lamUz + 1.0 / lamWs)
+        if self.addResidVar:
+            s11 = s11 + 1.0 / (num.LamSim[None, :] * lamWOs)
+        W = np.broadcast_to(self.model._w_pcs[None], (ns, pu, m)).reshape(ns * pu, m)
+        return ns, beta, lamz, dadd, s11.reshape(-1), np.ascontiguousarray(W)
+
+    def _w_pred(self):
+        torch = _lib.require_cuda()
+        num = self.model.num
+        pu = num.pu
+        npred = self.xpredt.shape[0]
+        ns, beta, lamz, dadd, s11, W = self._blocks()
+        self._pred = ops.Predictor(num.zt, W, beta, lamz, dadd, s11)
+        bad = int((self._pred.info != 0).sum().item())
+        if bad:
+            raise np.linalg.LinAlgError('%d of %d (sample, PC) covariance matrices are not positive definite' %
+                                        (bad, ns * pu))
+        joint = self.joint if self.joint is not None else (npred <= MAX_JOINT)
+        if joint and npred > 1:
+            mean, var, V = self._pred.predict(self.xpredt, want_V=True)
+            Sig = self._pred.pred_cov(self.xpredt, V)                 # (B, n, n)
+            del V
+        else:
+            mean, var = self._pred.predict(self.xpredt)
+            Sig = None
+        self.launches = 2 + (1 if Sig is not None else 0)
+        mean = mean.reshape(ns, pu, npred)
+        if self.storeMuSigma:
+            self.mu = mean.reshape(ns, pu * npred).cpu().numpy()
+            self.sigma = np.zeros((ns, pu * npred, pu * npred))
+            blk = (Sig.reshape(ns, pu, npred, npred).cpu().numpy() if Sig is not None
+                   else np.einsum('spt,tu->sptu', var.reshape(ns, pu, npred).cpu().numpy(), np.eye(npred)))
+            for j in range(pu):
+                sl = slice(j * npred, (j + 1) * npred)
+                self.sigma[:, sl, sl] = blk[:, j]
+        if self.storeRlz:
+            # one np.random.normal(size=npred*pu) per sample, in sample order, as SEPIA's rmultnormsvd
+            z = np.stack([np.random.normal(size=npred * pu) for _ in range(ns)])
+            zd = torch.as_tensor(z.reshape(ns, pu, npred), device='cuda')
+            if Sig is not None:
+                lam, Q = torch.linalg.eigh(Sig.reshape(ns, pu, npred, npred))
+                a = torch.sqrt(torch.clamp(lam, min=0.0)) * zd
+                dev = torch.einsum('spij,spj->spi', Q, a)
+            else:
+                dev = torch.sqrt(torch.clamp(var.reshape(ns, pu, npred), min=0.0)) * zd
+            w = (mean + dev).permute(0, 2, 1).contiguous()           # (ns, npred, pu)
+            self.w = w.cpu().numpy()
+
+    # ------------------------------------------------------------------ outputs
+    def get_w(self):
+        return self.w
+
+    def get_mu_sigma(self):
+        return self.mu, self.sigma
+
+    def get_y(self, std=False, device=False):
+        """(nsamp, npred, n_y) in native units (std=False); dtype follows self.w (callers cast w to
+        float32 first, assess_all_models.py:491).  device=True returns the torch CUDA tensor."""
+        torch = _lib.require_cuda()
+        sd = self.model.data.sim_data
+        w = np.asarray(self.w)
+        ns, npred, pu = w.shape
+        ysd = 1.0 if std else sd.orig_y_sd
+        ymu = 0.0 if std else sd.orig_y_mean
+        if self.model.data.scalar_out:
+            dt = torch.float32 if w.dtype == np.float32 else torch.float64
+            y = torch.as_tensor(w, device='cuda').to(dt) * torch.as_tensor(np.asarray(ysd), device='cuda').to(dt) \
+                + torch.as_tensor(np.asarray(ymu), device='cuda').to(dt)
+            y = y.reshape(ns, npred, -1)
+        elif w.dtype == np.float32:
+            y = ops.reconstruct(w.reshape(ns * npred, pu), sd.K, ysd, ymu).reshape(ns, npred, -1)
+        else:
+            Kd = torch.as_tensor(np.asarray(sd.K), device='cuda').double()
+            y = torch.as_tensor(w, device='cuda').double().reshape(ns * npred, pu) @ Kd
+            y = y * torch.as_tensor(np.asarray(ysd), device='cuda').double() + \
+                torch.as_tensor(np.asarray(ymu), device='cuda').double()
+            y = y.reshape(ns, npred, -1)
+        return y if device else y.cpu().numpy()
+
+
+class SepiaXvalEmulatorPrediction:
+    """Imported, never called, by the reference (assess_all_models.py:31-32)."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError('cross-validation prediction is not exercised by GladsGP and is out of scope')

@@ -61,7 +61,8 @@ int ggp_factor_unpack_f64(const double* factor_ws, int m, int B, double* L_dense
  * SepiaModel.mcmc_step / do_mcmc (A.4-A.6, A.10 mcmc_step), n_chains independent
  * chains of one model.  Parameter vector theta[P], P = d*pu + 2*pu + 1, in SEPIA's sampling order:
  * betaU in Fortran order (all d inputs of PC 0, then PC 1, ...), lamUz[pu], lamWs[pu], lamWOs.
- * Per-element tables have length P.  Enumerations:
+ * Per-element tables have length P.  fixed: 0 sampled, 1 fixed (SEPIA still draws the candidate, then
+ * rejects), 2 not in mcmcList (never visited, no draw).  Enumerations:
  *   prior_kind: 0 Uniform, 1 Gamma(a, b = rate), 2 Beta(a, b) on rho = exp(-x/4) (rho clamped to
  *               0.999), 3 Normal(a = mean, b = sd)
  *   prop_kind : 0 Uniform  x + step*U(-.5,.5);  1 BetaRho;  2 PropMH (Uniform when !do_propMH)

@@ -1,0 +1,166 @@
+"""GPU end-to-end through the reference-facing Python API (sepia.* mirror) vs the CPU oracle."""
+import os
+import numpy as np
+import pytest
+
+from helpers import so, svd_oracle, synthetic, make_problem, make_scalar_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(pr, q):
+    from sepia.SepiaData import SepiaData
+    from sepia.SepiaModel import SepiaModel
+    d = SepiaData(t_sim=pr['t'], y_sim=pr['y'], y_ind_sim=np.linspace(0, 1, pr['y'].shape[1]))
+    d.transform_xt(t_notrans=np.arange(q))
+    d.standardize_y(y_mean=pr['mu'], y_sd=pr['sd'])
+    d.create_K_basis(K=pr['K'])
+    return d, SepiaModel(d)
+
+
+def test_do_mcmc_follows_numpy_stream_like_oracle(cuda):
+    """Same seed -> same accept sequence and chain as the oracle driven by the same global stream,
+    and the global stream is left where SEPIA would leave it."""
+    pr = make_problem(m=64, q=3, pu=2)
+    data, model = _build(pr, 3)
+    om = so.OracleModel(so.OracleNum(pr['t'], data.sim_data.y_std, pr['K']))
+    # identical lamWOs prior (the oracle's residual sum differs at float32 round-off)
+    om.lamWOs.params = [p.copy() for p in model.params.lamWOs.prior.params]
+    np.random.seed(7)
+    om.do_mcmc(15, rng=np.random)
+    after_oracle = np.random.random_sample()
+    np.random.seed(7)
+    model.do_mcmc(15, prog=False)
+    after_gpu = np.random.random_sample()
+    assert after_gpu == after_oracle
+    ref = om.get_samples()
+    got = model.get_samples()
+    for k in ('betaU', 'lamUz', 'lamWs', 'lamWOs'):
+        assert got[k].shape == ref[k].shape
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-7)
+    np.testing.assert_allclose(got['logPost'], ref['logPost'], rtol=1e-7)
+    assert model.get_samples(5, nburn=3)['betaU'].shape == (5, 8)
+    np.testing.assert_allclose(model.logPost(), ref['logPost'][-1, 0], rtol=1e-7)
+
+
+def test_reference_fit_recipe_and_prediction(cuda, tmp_path):
+    """src/model.py:218-238 recipe (lamWOs override, tune, mcmc, save/restore) then the
+    assess_all_models.py:468-492 prediction pattern; moments vs oracle w_pred."""
+    from sepia.SepiaPredict import SepiaEmulatorPrediction
+    from gladsgp_b200 import model as gmodel
+    pr = make_problem(m=64, q=3, pu=2)
+    data, model = _build(pr, 3)
+    pc_prec = gmodel.pc_precision(data.sim_data)
+    w = np.dot(np.linalg.pinv(data.sim_data.K).T, data.sim_data.y_std.T).T
+    ref_prec = 1.0 / np.var(data.sim_data.y_std - np.dot(w, data.sim_data.K))
+    assert abs(pc_prec - ref_prec) < 1e-4 * ref_prec
+    gmodel.override_lamWOs(model, pc_prec)
+    np.random.seed(3)
+    model.tune_step_sizes(20, 5, prog=False)
+    assert np.all(model.params.betaU.mcmc.stepParam > 0)
+    model.do_mcmc(40, prog=False)
+    path = os.path.join(tmp_path, 'mod')
+    model.save_model_info(path)
+    import pickle
+    raw = pickle.load(open(path + '.pkl', 'rb'))
+    assert np.array(raw['samples']['betaU']).shape == (40, 4, 2)
+    data2, model2 = _build(pr, 3)
+    model2.restore_model_info(path)
+    samples = model2.get_samples(8, nburn=10)
+    for key in samples.keys():
+        samples[key] = samples[key].astype(np.float32)
+    tp = synthetic.test_design(4, 3)
+    np.random.seed(1)
+    preds = SepiaEmulatorPrediction(t_pred=tp, samples=samples, model=model2, storeMuSigma=True)
+    assert preds.w.shape == (8, 4, 2)
+    num = so.OracleNum(pr['t'], data.sim_data.y_std, pr['K'])
+    _, mu, Sig = so.w_pred(num, tp, samples, draw=False)
+    np.testing.assert_allclose(preds.mu, mu, rtol=1e-5, atol=1e-5 * np.abs(mu).max())
+    np.testing.assert_allclose(preds.sigma, Sig, rtol=1e-5, atol=1e-5 * np.abs(Sig).max())
+    preds.w = preds.w.astype(np.float32)
+    y = preds.get_y()
+    assert y.shape == (8, 4, pr['y'].shape[1]) and y.dtype == np.float32
+    ref = so.get_y(preds.w, pr['K'], pr['sd'].astype(np.float32), pr['mu'].astype(np.float32))
+    np.testing.assert_allclose(y, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_realisations_have_the_right_distribution(cuda):
+    from sepia.SepiaPredict import SepiaEmulatorPrediction
+    pr = make_problem(m=64, q=3, pu=2)
+    data, model = _build(pr, 3)
+    s1 = synthetic.posterior_samples(1, 4, 2, seed=2)
+    samples = {k: np.repeat(v, 4000, axis=0) for k, v in s1.items()}
+    tp = synthetic.test_design(3, 3)
+    np.random.seed(5)
+    preds = SepiaEmulatorPrediction(t_pred=tp, samples=samples, model=model, storeMuSigma=True)
+    mu, Sig = preds.mu[0], preds.sigma[0]
+    w = preds.w.transpose(0, 2, 1).reshape(4000, -1)          # (pu, npred) PC-major like mu
+    emp_mu = w.mean(axis=0); emp_cov = np.cov(w.T)
+    sd = np.sqrt(np.diag(Sig))
+    assert np.all(np.abs(emp_mu - mu) < 5 * sd / np.sqrt(4000))
+    np.testing.assert_allclose(emp_cov, Sig, atol=0.15 * np.outer(sd, sd).max())
+
+
+def test_scalar_model_api(cuda):
+    """fit_scalar_models.py:45-47,471-483 pattern (pu = 1, default priors, scalar standardisation)."""
+    from sepia.SepiaData import SepiaData
+    from sepia.SepiaModel import SepiaModel
+    from sepia.SepiaPredict import SepiaEmulatorPrediction
+    pr = make_scalar_problem(m=100)
+    data = SepiaData(t_sim=pr['t'], y_sim=pr['y'])
+    data.transform_xt()
+    data.standardize_y()
+    model = SepiaModel(data)
+    assert str(data).splitlines()[-1] == 'pu =     1 (univariate response dimension)'
+    np.random.seed(2)
+    model.do_mcmc(30, prog=False)
+    samples = model.get_samples(nburn=10, numsamples=8)
+    tp = np.linspace(0.05, 0.95, 50)[:, None]
+    preds = SepiaEmulatorPrediction(model=model, t_pred=tp, samples=samples, storeMuSigma=True)
+    y = preds.get_y()
+    assert y.shape == (8, 50, 1)
+    om_num = so.OracleNum(data.sim_data.t_trans, data.sim_data.y_std, None)
+    tt = (tp - data.sim_data.orig_t_min) / (data.sim_data.orig_t_max - data.sim_data.orig_t_min)
+    _, mu, Sig = so.w_pred(om_num, tt, samples, draw=False)
+    np.testing.assert_allclose(preds.mu, mu, rtol=1e-6, atol=1e-6 * np.abs(mu).max())
+    np.testing.assert_allclose(preds.sigma, Sig, rtol=1e-6, atol=1e-6 * np.abs(Sig).max())
+
+
+def test_fixed_parameter_and_uniform_prior(cuda):
+    """include_trunc_error.py:76-83 pattern."""
+    from sepia.SepiaPrior import SepiaPrior
+    pr = make_problem(m=64, q=3, pu=2)
+    data, model = _build(pr, 3)
+    var = 77.0
+    model.params.lamWOs.fixed = np.array([[True]])
+    model.params.lamWOs.val = np.array([[var]])
+    model.params.lamWOs.prior = SepiaPrior(model.params.lamWOs, dist='Uniform', params=[0, 2 * var], bounds=[0, 2 * var])
+    np.random.seed(0)
+    model.tune_step_sizes(10, 4, prog=False)
+    model.do_mcmc(12, prog=False)
+    s = model.get_samples()
+    assert np.all(s['lamWOs'] == var)
+    assert len(np.unique(s['betaU'][:, 0])) > 1
+
+
+def test_randomized_svd_matches_reference_algorithm(cuda):
+    from gladsgp_b200 import svd
+    pr = make_problem(m=100, q=4, pu=3, n_x=60, n_t=50)
+    X = pr['y_std'].astype(np.float32)
+    rng = np.random.RandomState(4)
+    omega = rng.normal(size=(X.shape[1], 25)).astype(np.float32)
+    Ur, Sr, Vr = svd_oracle.randomized_svd(X, 25, k=0, q=1, omega=omega)
+    U, S, Vh = svd.randomized_svd(X, 25, k=0, q=1, omega=omega)
+    assert U.shape == Ur.shape and S.shape == Sr.shape and Vh.shape == Vr.shape
+    np.testing.assert_allclose(S[:10], Sr[:10], rtol=2e-4)
+    for i in range(5):           # leading vectors up to sign
+        sgn = np.sign(np.dot(Vh[i], Vr[i]))
+        np.testing.assert_allclose(sgn * Vh[i], Vr[i], atol=5e-3 * np.abs(Vr[i]).max() + 1e-4)
+        np.testing.assert_allclose(sgn * U[:, i], Ur[:, i], atol=5e-3)
+    rec = (U * S) @ Vh
+    recr = (Ur * Sr) @ Vr
+    assert np.linalg.norm(rec - recr) < 2e-3 * np.linalg.norm(recr)
+    # global-stream consumption is the reference's: one normal(size=(n, p+k)) draw
+    np.random.seed(9); svd.randomized_svd(X, 5, k=0, q=1); a = np.random.random_sample()
+    np.random.seed(9); np.random.normal(size=(X.shape[1], 5)); b = np.random.random_sample()
+    assert a == b
