@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the GP-emulator hot path (contract: see the task brief / DESIGN.md section 6).
+
+Metric (BASELINE.json): MCMC steps/s at m=512, q=8 (d=9), pu=10 -- one step = one SEPIA
+mcmc_step = pu*(d+4) fused covariance+Cholesky block evaluations per chain.  A bench "step"
+advances every chain of every rank by one mcmc_step; `value` = chain-steps per second over the
+whole job.  Chains are independent (weak scaling: a fixed number of chains per GPU, no data-path
+collective; one NCCL all_gather of the per-chain log-posteriors at the end).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--chains C]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M, Q, PU = 512, 8, 10
+D = Q + 1
+P = D * PU + 2 * PU + 1
+EVALS_PER_STEP = PU * (D + 4)
+METRIC = 'mcmc_steps_per_s'
+UNIT = 'chain-steps/s'
+WORKLOAD = 'cfg3 multivariate PCA emulator: m=512 sims, q=8 params (d=9), pu=10 PCs, SEPIA Metropolis-within-Gibbs'
+
+
+def build_problem(n_x, n_t, seed=20240318 + 3, standardized=True):
+    """Synthetic GlaDS-shaped ensemble (+ column mean / clamped sd as src/model.py:60-64)."""
+    from gladsgp_b200 import synthetic
+    t = synthetic.design(M, Q, seed=20240318)
+    y = synthetic.ensemble(t, n_x=n_x, n_t=n_t, seed=seed)
+    mu = np.mean(y, axis=0)
+    sd = np.std(y, ddof=1, axis=0)
+    sd[sd < 1e-6] = 1e-6
+    if not standardized:
+        return t, y, mu.astype(np.float32), sd.astype(np.float32)
+    return t, y, ((y - mu) / sd).astype(np.float32), mu.astype(np.float32), sd.astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nme, v in zip(names, r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def oracle_model(t, y_std, K, pc_prec, resid_ss=None):
+    from oracle import sepia_oracle as so
+    num = so.OracleNum(t, y_std, K, resid_ss=resid_ss)
+    om = so.OracleModel(num)
+    om.override_lamWOs(pc_prec)
+    return om
+
+
+def cpu_steps_per_s(om, n_steps, seed=1):
+    rng = np.random.RandomState(seed)
+    t0 = time.perf_counter()
+    om.do_mcmc(n_steps, rng=rng)
+    dt = time.perf_counter() - t0
+    return n_steps / dt, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def small_setup(n_x, n_t):
+    """Host-only set-up for the reference arm (no GPU): K from the oracle rSVD on a reduced field."""
+    from oracle import svd_oracle
+    t, y, y_std, mu, sd = build_problem(n_x, n_t)
+    U, S, Vh = svd_oracle.randomized_svd(y_std, 25, k=0, q=1, rng=np.random.RandomState(0))
+    K = svd_oracle.k_basis(S, Vh, PU, M).astype(np.float32)
+    w = np.dot(np.linalg.pinv(K).T, y_std.T).T
+    pc_prec = 1.0 / np.var(y_std - np.dot(w, K))
+    return t, y_std, K, pc_prec
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (NumPy/SciPy SEPIA restatement in
+    oracle/, `kind: port` -- the sepia package itself is not installable here), all host threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t, y_std, K, pc_prec = small_setup(args.ref_nx, args.ref_nt)
+    om = oracle_model(t, y_std, K, pc_prec)
+    rng = np.random.RandomState(1)
+    om.do_mcmc(args.warmup, rng=rng)
+    t0 = time.perf_counter()
+    om.do_mcmc(args.steps, rng=rng)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    cores = blas_threads()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'chains': 1, 'field_n_y_for_setup': args.ref_nx * args.ref_nt,
+                   'evals_per_step': EVALS_PER_STEP},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d mcmc_steps of one chain (oracle/sepia_oracle.py, NumPy/SciPy FP64, %d BLAS threads)'
+                                   % (args.steps, cores)},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def fp64_peak_tflops(torch):
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device='cuda'); b = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    torch.matmul(a, b); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / best / 1e9
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from gladsgp_b200 import svd, model as gmodel, ops
+    from sepia.SepiaData import SepiaData
+    from sepia.SepiaModel import SepiaModel
+
+    # ---------------- set-up through the public API (untimed): standardise, rSVD, K, SepiaModel
+    t_set = time.perf_counter()
+    nx = args.nx if (world == 1 or rank == 0) else max(args.nx // 10, 64)   # host RAM: one full field per box
+    t, y, mu, sd = build_problem(nx, args.nt, standardized=False)
+    data = SepiaData(t_sim=t, y_sim=y, y_ind_sim=np.linspace(0, 1, y.shape[1]))
+    data.transform_xt(t_notrans=np.arange(Q))
+    data.standardize_y(y_mean=mu, y_sd=sd)
+    np.random.seed(1234)
+    torch.cuda.synchronize(); t_svd = time.perf_counter()
+    U, S, Vh = svd.randomized_svd(data.sim_data.y_std, 25, k=0, q=1)
+    torch.cuda.synchronize(); svd_s = time.perf_counter() - t_svd
+    K = ((S[:PU, None] * Vh[:PU]) / np.sqrt(M)).astype(np.float32)
+    data.create_K_basis(K=K)
+    model = SepiaModel(data)
+    pc_prec = gmodel.pc_precision(data.sim_data)
+    gmodel.override_lamWOs(model, pc_prec)
+    setup_s = time.perf_counter() - t_set
+    chains = args.chains
+
+    # ---------------- device-resident timing (`value`): inputs already in HBM
+    eng, tb = model._get_engine(chains)
+    rs = np.random.RandomState(100 + rank)
+    nsteps_tot = args.warmup + args.steps
+    us = torch.as_tensor(rs.random_sample((chains, 2 * P * nsteps_tot))).to('cuda')
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = eng.run(args.warmup, tb['step'], uniforms=us[:, :2 * P * args.warmup].contiguous(), record=False)
+    us_t = us[:, 2 * P * args.warmup:].contiguous()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = eng.run(args.steps, tb['step'], uniforms=us_t, init_sigwl=False, record=True, time_kernels=True)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = e0.elapsed_time(e1)
+    sweep_ms, wos_ms = out['kernel_ms']
+    n_valid = int(out['eval_count'][0])                              # block evaluations inside the sweep launches
+    lp_last = out['lp'][-1].clone()
+
+    # ---------------- end-to-end through the public API with host buffers (`e2e`)
+    np.random.seed(4321 + rank)
+    model.do_mcmc_chains(args.warmup, chains)                         # warm the path
+    barrier()
+    t0 = time.perf_counter()
+    draws, lps = model.do_mcmc_chains(args.steps, chains)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = 2 * P * chains * 8
+    d2h = (P + 1) * chains * 8 + 8 * chains / max(args.steps, 1)
+
+    tm = torch.tensor([dev_ms, e2e_s * 1e3, sweep_ms, wos_ms], dtype=torch.float64, device='cuda')
+    cnt = torch.tensor([float(n_valid)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        gathered = [torch.empty_like(lp_last) for _ in range(world)]
+        dist.all_gather(gathered, lp_last)                            # the path's one collective: log-posteriors
+    dev_ms, e2e_ms, sweep_ms, wos_ms = [float(x) for x in tm.cpu()]
+    n_valid_all = float(cnt.cpu()[0])
+
+    if rank == 0:
+        total_chains = chains * world
+        value = total_chains * args.steps / (dev_ms * 1e-3)
+        e2e_val = total_chains * args.steps / (e2e_ms * 1e-3)
+        # roofline of the dominant kernel (sweep_kernel): algorithmic FP64 flops per evaluated site
+        # = m^3/3 + m^2 + 2m (Cholesky + solve) + (3d+2) m(m-1)/2 (covariance build)
+        flop_eval = M ** 3 / 3.0 + M * M + 2 * M + (3 * D + 2) * M * (M - 1) / 2.0
+        sweep_evals = n_valid_all / world          # counted on the device (per-rank average)
+        achieved = sweep_evals * flop_eval / (sweep_ms * 1e-3) / 1e12
+        peak = fp64_peak_tflops(torch)
+        # CPU baseline: the oracle port on this box's host cores, bounded sample
+        om = oracle_model(t, data.sim_data.y_std, K, pc_prec, resid_ss=0.0)
+        cpu_val, cpu_dt = cpu_steps_per_s(om, args.cpu_steps)
+        cores = blas_threads()
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'chains_per_gpu': chains, 'chains_total': total_chains,
+                       'evals_per_step_per_chain': EVALS_PER_STEP, 'field_n_y': int(y.shape[1]),
+                       'l2': 'working set (factor workspaces %d MB/GPU) exceeds L2; no flush needed'
+                             % (chains * PU * ops._lib.load().ggp_factor_doubles(M) * 8 >> 20),
+                       'rsvd_setup_s': svd_s, 'setup_s': setup_s},
+            'single_chain_equiv_steps_per_s': value / total_chains,
+            'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(d2h),
+                    'api': 'SepiaModel.do_mcmc_chains (host np.random stream -> device, draws -> host)'},
+            'gpu_launches': 4 * args.steps,
+            'roofline': {'bound': 'tensor', 'kernel': 'ggp::sweep_kernel (fused cov build + DMMA Cholesky + solve)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                         'peak_source': 'cuBLAS FP64 GEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
+                         'traffic': None, 'evals_in_timed_launches': sweep_evals, 'kernel_ms_total': sweep_ms,
+                         'kernel_share_of_step': sweep_ms / dev_ms, 'flop_per_eval': flop_eval},
+            'cpu_baseline': {'value': cpu_val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d mcmc_steps of one chain in %.1f s (oracle/sepia_oracle.py, NumPy/SciPy FP64)'
+                                       % (args.cpu_steps, cpu_dt)},
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--chains', type=int, default=74, help='independent chains per GPU (74*10 CTAs = 5 waves of 148 SMs)')
+    ap.add_argument('--nx', type=int, default=4000, help='field nodes (cfg3: 4k)')
+    ap.add_argument('--nt', type=int, default=365, help='field time steps (cfg3: 365)')
+    ap.add_argument('--ref-nx', type=int, default=400)
+    ap.add_argument('--ref-nt', type=int, default=36)
+    ap.add_argument('--cpu-steps', type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

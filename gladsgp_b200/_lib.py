@@ -28,6 +28,7 @@ class McmcArgs(C.Structure):
         ('r_cand', C.c_void_p), ('r_logacorr', C.c_void_p), ('r_logu', C.c_void_p), ('r_valid', C.c_void_p),
         ('draws', C.c_void_p), ('lp_draws', C.c_void_p), ('accepted', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+        ('eval_count', C.c_void_p), ('kernel_ms', C.c_void_p),
     ]
 
 

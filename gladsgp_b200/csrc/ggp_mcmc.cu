@@ -144,6 +144,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
         __syncthreads();
         const double ll_new = eval_block_loglik(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, nullptr, nullptr);
         if (threadIdx.x == 0) {
+            if (a.eval_count) atomicAdd(a.eval_count, 1ULL);
             const double ll_old = sig[j];
             const double xold = th[s];
             const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], cand) -
@@ -188,6 +189,7 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
     if (threadIdx.x == 0) {
         if (mode == 0) a.sigwl[(size_t)c * pu + j] = ll;
         else sig_cand[(size_t)c * pu + j] = ll;
+        if (a.eval_count) atomicAdd(a.eval_count + 1, 1ULL);
     }
 }
 
@@ -304,13 +306,37 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         eval_all_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, 0);
         GGP_CUDA(cudaGetLastError());
     }
+    // optional per-kernel device timing (CUDA events on the launching stream)
+    const bool timed = a.kernel_ms != nullptr && a.n_steps > 0;
+    cudaEvent_t* ev = nullptr;
+    if (timed) {
+        ev = new cudaEvent_t[3 * (size_t)a.n_steps];
+        for (int i = 0; i < 3 * a.n_steps; ++i) cudaEventCreate(&ev[i]);
+    }
     for (int t = 0; t < a.n_steps; ++t) {
         plan_kernel<<<cb, 32, 0, st>>>(a, pl, t);
+        if (timed) cudaEventRecord(ev[3 * t + 0], st);
         sweep_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
+        if (timed) cudaEventRecord(ev[3 * t + 1], st);
         eval_all_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, 1);
+        if (timed) cudaEventRecord(ev[3 * t + 2], st);
         finalize_kernel<<<cb, 32, 0, st>>>(a, pl, sig_cand, t);
     }
-    GGP_CUDA(cudaGetLastError());
+    cudaError_t le = cudaGetLastError();
+    if (timed) {
+        cudaStreamSynchronize(st);
+        double sw = 0.0, wo = 0.0;
+        for (int t = 0; t < a.n_steps; ++t) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[3 * t + 0], ev[3 * t + 1]); sw += ms;
+            cudaEventElapsedTime(&ms, ev[3 * t + 1], ev[3 * t + 2]); wo += ms;
+        }
+        a.kernel_ms[0] = sw;      // total sweep_kernel time (ms)
+        a.kernel_ms[1] = wo;      // total eval_all_kernel (lamWOs wave) time (ms)
+        for (int i = 0; i < 3 * a.n_steps; ++i) cudaEventDestroy(ev[i]);
+        delete[] ev;
+    }
+    if (le != cudaSuccess) return cuda_fail(le, "mcmc launches");
     return GGP_OK;
 }
 

@@ -127,7 +127,7 @@ class McmcEngine:
         self.theta.copy_(th)
 
     def run(self, n_steps, step, uniforms=None, replay=None, do_propMH=True, init_sigwl=True,
-            record=True, record_accept=False):
+            record=True, record_accept=False, time_kernels=False):
         """step: (P,) or (n_steps,P) or (n_chains,P) [see step_axes] numpy/tensor of step sizes.
         uniforms: (n_chains, n_uniform) U[0,1) stream, or replay = dict(cand, logacorr, logu, valid)
         each (n_steps, n_chains, P).  Returns dict(draws, lp, accepted, consumed)."""
@@ -180,9 +180,17 @@ class McmcEngine:
             acc = torch.empty((n_steps, self.n_chains, self.P), dtype=torch.uint8, device=dev)
             a.accepted = acc.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        kms = (C.c_double * 2)(0.0, 0.0)
+        cnt = None
+        if time_kernels:
+            a.kernel_ms = C.cast(kms, C.c_void_p)
+            cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+            a.eval_count = cnt.data_ptr()
         check(self.lib.ggp_mcmc_run_f64(C.byref(a), stream_ptr()), 'ggp_mcmc_run_f64')
         self._keep = keep
-        return dict(draws=draws, lp=lp, accepted=acc, consumed=self.upos)
+        return dict(draws=draws, lp=lp, accepted=acc, consumed=self.upos,
+                    kernel_ms=(kms[0], kms[1]) if time_kernels else None,
+                    eval_count=cnt.cpu().numpy() if cnt is not None else None)
 
 
 class Predictor:

@@ -84,7 +84,10 @@ class SepiaModel:
             w = np.linalg.solve(G, YK.T).T
             num.LamSim = np.diag(G).copy()
             # ||y_std - w K||^2 without forming the residual matrix
-            ss_y = float(np.einsum('ij,ij->', ys, ys, dtype=np.float64))
+            ss_y = 0.0
+            for c0 in range(0, n_y, 1 << 16):
+                blk = ys[:, c0:c0 + (1 << 16)].astype(np.float64)
+                ss_y += float(np.sum(blk * blk))
             resid_ss = max(ss_y - 2.0 * float(np.sum(w * YK)) + float(np.sum((w @ G) * w)), 0.0)
         num.w = w.reshape((-1, 1), order='F')           # PC-major stack
         self._w_pcs = np.ascontiguousarray(w.T)         # (pu, m)
@@ -301,7 +304,9 @@ class SepiaModel:
                 continue
             coef = _logit_glm(np.log(ladder[:, e]), acc[:, e].astype(np.float64), n_burn)
             if coef is not None and np.all(np.isfinite(coef)) and coef[1] < 0:
-                new_step[e] = np.exp((target - coef[0]) / coef[1])
+                lg = (target - coef[0]) / coef[1]
+                if np.isfinite(lg) and abs(lg) < 600.0:
+                    new_step[e] = np.exp(lg)
         o = 0
         for b, v0, v1 in zip(blocks, saved, final_blocks):
             n = b.val.size

@@ -105,6 +105,11 @@ typedef struct ggp_mcmc_args {
     unsigned char* accepted;
     void* workspace;
     size_t workspace_bytes;
+    unsigned long long* eval_count; /* device, nullable: [2] += block evaluations done by the sweep launches
+                              and by the init / lamWOs-wave launches */
+    double* kernel_ms;     /* HOST pointer, nullable: [2] receives total device time (ms, CUDA events on
+                              `stream`) of the sweep launches and of the lamWOs-wave launches; makes the
+                              call synchronous */
 } ggp_mcmc_args;
 
 long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains);

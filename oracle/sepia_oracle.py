@@ -38,7 +38,7 @@ import scipy.linalg
 class OracleNum:
     """Numeric set-up of a sim-only SepiaModel (SepiaModel.__init__ upstream)."""
 
-    def __init__(self, t_trans, y_std, K=None):
+    def __init__(self, t_trans, y_std, K=None, resid_ss=None):
         t_trans = np.asarray(t_trans)
         y_std = np.asarray(y_std)
         if y_std.ndim == 1:
@@ -68,6 +68,8 @@ class OracleNum:
         self.n_y = y_std.shape[1]
         if self.scalar_out:
             self.resid_ss = 0.0
+        elif resid_ss is not None:
+            self.resid_ss = float(resid_ss)     # caller-supplied (skips the m x n_y residual pass)
         else:
             r = y_std - np.dot(self.w, self.K)
             self.resid_ss = float(np.sum(np.square(r, dtype=np.float64)))
