@@ -45,6 +45,7 @@ SIGNATURES = {
     'ggp_padded_m': (_I, [_I]),
     'ggp_loglik_batched_f64': (_I, [_P, _I, _I, _P, _LL, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     'ggp_factor_unpack_f64': (_I, [_P, _I, _I, _P, _P]),
+    'ggp_sizeof_mcmc_args': (_I, []),
     'ggp_mcmc_workspace_bytes': (_LL, [_I, _I, _I, _I]),
     'ggp_mcmc_run_f64': (_I, [C.POINTER(McmcArgs), _P]),
     'ggp_predict_workspace_bytes': (_LL, [_I, _I, _I]),
@@ -70,6 +71,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
+    if lib.ggp_sizeof_mcmc_args() != C.sizeof(McmcArgs):
+        raise GgpError('ggp_mcmc_args layout mismatch between _lib.py and the library')
     _lib = lib
     return lib
 

@@ -245,6 +245,8 @@ using namespace ggp;
 
 extern "C" {
 
+int ggp_sizeof_mcmc_args(void) { return (int)sizeof(ggp_mcmc_args); }
+
 long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains)
 {
     if (m <= 0 || d <= 0 || pu <= 0 || n_chains <= 0) return -1;

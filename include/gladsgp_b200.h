@@ -112,6 +112,7 @@ typedef struct ggp_mcmc_args {
                               call synchronous */
 } ggp_mcmc_args;
 
+int ggp_sizeof_mcmc_args(void);   /* sizeof(ggp_mcmc_args), for binding self-checks */
 long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains);
 int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream);
 

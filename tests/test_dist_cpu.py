@@ -1,0 +1,59 @@
+"""CPU, world_size 2 over gloo: sharding by independent unit and the one gather of the path."""
+import os
+import socket
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ROOT  # noqa: F401
+from gladsgp_b200.dist import shard_bounds, all_gather_concat
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 74, 100000):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    # chains sharded across ranks: every rank owns a contiguous slice and produces its per-chain values
+    n_chains, n = 7, 11
+    lo, hi = shard_bounds(n_chains, rank, world)
+    lp = torch.arange(lo, hi, dtype=torch.float64) * 10.0
+    full = all_gather_concat(lp)
+    # prediction sharded by design block: (B, n_local) moments gathered along the design axis
+    dlo, dhi = shard_bounds(n, rank, world)
+    mean = torch.arange(3, dtype=torch.float64)[:, None] * 100 + torch.arange(dlo, dhi, dtype=torch.float64)[None, :]
+    allm = all_gather_concat(mean, dim=1)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max-over-ranks timing reduction used by bench.py
+    q.put((rank, full.numpy(), allm.numpy(), float(t)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp_mean = np.arange(3)[:, None] * 100.0 + np.arange(11)[None, :]
+    for rank, full, allm, tmax in res:
+        np.testing.assert_array_equal(full, np.arange(7) * 10.0)
+        np.testing.assert_array_equal(allm, exp_mean)
+        assert tmax == 2.0

@@ -1,0 +1,47 @@
+"""GPU vs the committed golden fixtures (no oracle call; runs where /root/reference does not exist)."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_gpu_matches_sepia_golden(cuda):
+    from gladsgp_b200 import ops
+    g = np.load(os.path.join(GOLD, 'sepia_oracle.npz'))
+    m = g['zt'].shape[0]
+    js = g['js'].astype(int)
+    dadd = 1.0 / (g['LamSim'][js] * g['lamwos']) + 1.0 / g['lamws']
+    W = g['w'].T[js]
+    C = ops.cov_build(g['zt'], g['beta'], g['lamz'], dadd).cpu().numpy()
+    np.testing.assert_allclose(C, g['C'], rtol=1e-13)
+    ll = ops.loglik_batched(g['zt'], W, g['beta'], g['lamz'], dadd)['loglik'].cpu().numpy()
+    np.testing.assert_allclose(ll, g['loglik'], rtol=1e-8)
+    tb = {k[3:]: g[k] for k in g.files if k.startswith('tb_')}
+    eng = ops.McmcEngine(g['zt'], np.ascontiguousarray(g['w'].T), g['LamSim'], tb, n_chains=1)
+    eng.set_state(tb['theta'])
+    replay = {k[3:]: g[k] for k in g.files if k.startswith('rp_')}
+    out = eng.run(6, tb['step'], replay=replay, record_accept=True)
+    assert np.array_equal(out['accepted'].cpu().numpy(), g['chain_acc'])
+    assert np.array_equal(out['draws'].cpu().numpy()[:, 0, :], g['chain_draws'])
+    np.testing.assert_allclose(out['lp'].cpu().numpy()[:, 0], g['chain_lp'], rtol=1e-9)
+
+
+def test_gpu_rsvd_matches_reference_svd_py_golden(cuda):
+    """Same seeded global stream as the fixture (drawn by the reference's own src/svd.py)."""
+    from gladsgp_b200 import svd
+    g = np.load(os.path.join(GOLD, 'rsvd_reference.npz'))
+    X = g['X']
+    for tag in ('a', 'b', 'c'):
+        p, k, q = [int(v) for v in g['pkq_' + tag]]
+        k = None if k < 0 else k
+        np.random.seed(1000 + p)
+        U, S, Vh = svd.randomized_svd(X, p, k=k, q=q)
+        assert U.shape == g['U_' + tag].shape and S.shape == g['S_' + tag].shape and Vh.shape == g['Vh_' + tag].shape
+        np.testing.assert_allclose(S, g['S_' + tag], rtol=5e-4)
+        nz = np.where(g['S_' + tag] > 1e-2 * g['S_' + tag][0])[0]
+        for i in nz:
+            sgn = np.sign(np.dot(Vh[i], g['Vh_' + tag][i]))
+            np.testing.assert_allclose(sgn * Vh[i], g['Vh_' + tag][i], atol=5e-3)
+            np.testing.assert_allclose(sgn * U[:, i], g['U_' + tag][:, i], atol=5e-3)
