@@ -41,6 +41,7 @@ SIGNATURES = {
     'ggp_device_info': (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_LL)]),
     'ggp_cov_build_f64': (_I, [_P, _I, _I, _P, _P, _P, _I, _P, _P]),
     'ggp_cross_cov_f64': (_I, [_P, _I, _P, _I, _I, _P, _P, _I, _P, _P]),
+    'ggp_debug_exp_neg_f64': (_I, [_P, _P, _I, _P]),
     'ggp_factor_doubles': (_LL, [_I]),
     'ggp_padded_m': (_I, [_I]),
     'ggp_loglik_batched_f64': (_I, [_P, _I, _I, _P, _LL, _P, _P, _P, _I, _P, _P, _P, _P, _P]),

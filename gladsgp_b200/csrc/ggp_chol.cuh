@@ -6,48 +6,86 @@
 // (SURVEY.md 8a rows a3+a4 / Appendix A.10 cov_self, do_loglik, log_lik; called from
 //  /root/reference/src/model.py:234-235 through sepia).
 //
-// Algorithm: left-looking blocked Cholesky, panel width 32.  For panel j the CTA
-//   1. accumulates S = L[rows, 0:32j] * L[panel rows, 0:32j]^T on the FP64 tensor cores
-//      (DMMA.8x8x4, accumulators in registers; A/B fragments are 16-byte loads straight from the
-//      packed factor, which lives in global memory and stays L2 resident),
-//   2. builds the covariance entries of the panel on the fly (exp fused in, nothing read from HBM)
-//      and forms P = C - S in shared memory,
-//   3. factors the 32x32 diagonal block with one warp (row per lane, shuffle broadcast of pivots),
-//   4. solves the rows below with one thread per row, and updates the running forward solve of w,
-//   5. writes the finished panel into the packed factor.
-// The covariance matrix itself never exists in memory.
+// Algorithm: left-looking blocked Cholesky, panel width 32, 256 threads, two CTAs per SM so that the
+// serial diagonal-block phase of one matrix overlaps the tensor-core phase of another.  For panel j:
+//   1. S = L[rows, 0:32j] * L[panel rows, 0:32j]^T on the FP64 tensor cores (DMMA.8x8x4), accumulators
+//      in registers, A/B fragments are 16-byte loads straight from the packed factor (L2 resident);
+//   2. covariance entries of the panel computed in the accumulator layout (exp fused, nothing read
+//      from HBM), P = C - S stays in registers;
+//   3. the 32x32 diagonal block goes through shared memory: warp 0 factors it (row per lane), then
+//      warp 0 forward-solves the w block and stores the diagonal rows while warp 1 inverts the block
+//      (32 independent forward substitutions);
+//   4. X = P * Minv^T again on DMMA: the accumulator fragments of step 2 are valid A fragments under a
+//      permutation of the k index, so no data movement is needed; X is stored to the packed factor
+//      straight from the fragments and the running forward solve of w is updated.
+// The covariance matrix itself never exists in memory.  The serial phase is written as compact loops
+// over shared memory: a fully unrolled register version made the kernel 200 KB of SASS and
+// instruction-fetch bound (profiles/r1b_*).
 #pragma once
 #include "ggp_common.cuh"
 
 namespace ggp {
 
 struct EvalSmem {
-    double* LT;     // [32][LT_LD] transposed diagonal factor: LT[k][i] = L[i][k]
-    double* rdiag;  // [32] reciprocal pivots
-    double* uj;     // [32] forward-solve block
-    double* red;    // [8]  scratch / broadcast
-    double* Ps;     // [PASS_ROWS][PS_LD]
+    double* D;      // [32][D_LD]   diagonal block: P on entry, rows of Ljj after the factorisation
+    double* LT;     // [32][LT_LD]  LT[k][i] = L[i][k]
+    double* Minv;   // [32][MI_LD]  Minv[c][k] = (Ljj^-1)[c][k]
+    double* rdiag;  // [32]
+    double* uj;     // [32]
+    double* red;    // [8]
+    double* etab;   // [32] 2^(j/32)
     double* wres;   // [Mp]
-    double* S;      // [Mp][d] sqrt(beta)-scaled coordinates
+    double* ST;     // [d][Mp] sqrt(beta)-scaled coordinates, transposed
     int* flag;      // [4]
 };
 
 __host__ __device__ inline size_t eval_smem_bytes(int Mp, int d) {
-    return (size_t)(32 * LT_LD + 32 + 32 + 8 + PASS_ROWS * PS_LD + Mp + (size_t)Mp * d) * sizeof(double) + 16;
+    return (size_t)(32 * D_LD + 32 * LT_LD + 32 * MI_LD + 32 + 32 + 8 + 32 + Mp + (size_t)Mp * d) * sizeof(double) + 16;
 }
 
 __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     EvalSmem s;
     double* p = reinterpret_cast<double*>(base);
+    s.Minv = p;     p += 32 * MI_LD;
     s.LT = p;       p += 32 * LT_LD;
     s.rdiag = p;    p += 32;
     s.uj = p;       p += 32;
     s.red = p;      p += 8;
-    s.Ps = p;       p += PASS_ROWS * PS_LD;
+    s.etab = p;     p += 32;
     s.wres = p;     p += Mp;
-    s.S = p;        p += (size_t)Mp * d;
+    s.ST = p;       p += (size_t)Mp * d;
+    s.D = p;        p += 32 * D_LD;
     s.flag = reinterpret_cast<int*>(p);
     return s;
+}
+
+// exp(y) for y <= 0, ~1 ulp: y = (32 n + j) ln2/32 + r, |r| <= ln2/64, exp(y) = 2^n * 2^(j/32) * p(r).
+// 12 FP64 operations (libdevice exp: ~25) and a fraction of its code size.  Results below 1e-300 flush to 0
+// (covariance entries that small cannot influence any result at 1e-8).
+__device__ __forceinline__ double exp_neg(double y, const double* __restrict__ etab)
+{
+    const double t = fma(y, 46.166241308446828384, 6755399441055744.0);     // 32/ln2, 1.5*2^52
+    const int n32 = __double2loint(t);
+    const double fn = t - 6755399441055744.0;
+    double r = fma(fn, -0.021660849390173098, y);                              // ln2/32 high part (low 20 mantissa bits zero)
+    r = fma(fn, -2.325192846878874e-12, r);                                     // ln2/32 low part
+    double p = 1.9841269841269841e-04;                                          // 1/5040
+    p = fma(p, r, 1.3888888888888889e-03);
+    p = fma(p, r, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = p * etab[n32 & 31];
+    const int n = n32 >> 5;
+    const double res = __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
+    return (y < -690.0) ? 0.0 : res;
+}
+
+__device__ inline void fill_exp_table(double* etab)
+{
+    if (threadIdx.x < 32) etab[threadIdx.x] = exp2((double)threadIdx.x * 0.03125);
 }
 
 // S += A[rows, 0:32j] * Lb[panel rows, 0:32j]^T for NU 8-row units of one warp (DMMA.8x8x4).
@@ -55,9 +93,9 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
 // indexed by local row), B-operand rows from the packed factor `Lb`.  NU is a template parameter so
 // that no predicated-off DMMA is ever issued (a predicated-off DMMA still occupies the pipe).
 template <int NU>
-static __device__ __forceinline__ void panel_gemm(double (&acc)[4][4][2], const double* __restrict__ Ap,
+static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const double* __restrict__ Ap,
                                                   const double* __restrict__ Lb, int Mp, int j, int row0,
-                                                  const int (&rb)[4], int g, int q, int a_ld)
+                                                  const int (&rb)[2], int g, int q, int a_ld)
 {
     const int nsl = 4 * j;
     auto a_slab = [&](int s) -> const double* {
@@ -97,6 +135,56 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[4][4][2], const 
     }
 }
 
+// One 8-row unit: X = P * Minv^T on DMMA.  p[cb][e] (accumulator layout) doubles as the A fragment.
+static __device__ __forceinline__ void unit_trsm(const double (&p)[4][2], double (&x)[4][2],
+                                                 const double* __restrict__ Minv, int g, int q)
+{
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+        x[cb][0] = 0.0; x[cb][1] = 0.0;
+#pragma unroll
+        for (int kb = 0; kb <= cb; ++kb) {
+            const double2 b = *reinterpret_cast<const double2*>(Minv + (8 * cb + g) * MI_LD + 8 * kb + 2 * q);
+            dmma884(x[cb][0], x[cb][1], p[kb][0], b.x);
+            dmma884(x[cb][0], x[cb][1], p[kb][1], b.y);
+        }
+    }
+}
+
+// Covariance entries of one unit (8 rows x 32 panel columns) in the accumulator layout: p = C - p.
+// row_is_train: rows index training points (self covariance, with diagonal / padding rules);
+// otherwise rows index a separate coordinate array (cross covariance) and `nrow_valid` masks padding.
+static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double* __restrict__ RT, int rld, int r,
+                                                bool row_ok, const double* __restrict__ ST, int Mp, int d, int m,
+                                                int row0, int q, double inv_lamz, double diag, bool self,
+                                                const double* __restrict__ etab)
+{
+    double dist[4][2];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) { dist[cb][0] = 0.0; dist[cb][1] = 0.0; }
+    for (int k = 0; k < d; ++k) {
+        const double sr = RT[(size_t)k * rld + r];
+        const double* sc = ST + (size_t)k * Mp + row0 + 2 * q;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const double2 c2 = *reinterpret_cast<const double2*>(sc + 8 * cb);
+            const double t0 = sr - c2.x, t1 = sr - c2.y;
+            dist[cb][0] = fma(t0, t0, dist[cb][0]);
+            dist[cb][1] = fma(t1, t1, dist[cb][1]);
+        }
+    }
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = row0 + 8 * cb + 2 * q + e;
+            double v = (row_ok && c < m) ? exp_neg(-dist[cb][e], etab) * inv_lamz : 0.0;
+            if (self && r == c) v = (r < m) ? diag : 1.0;
+            p[cb][e] = v - p[cb][e];
+        }
+    }
+}
+
 // Whole-CTA evaluation (NT threads).  Returns the block log-likelihood term to every thread;
 // *info (if non-null, written by thread 0) = 0 or 1-based index of the failing pivot.
 // beta may point to global or shared memory.  Lp is the packed-factor workspace (packed_doubles(Mp)).
@@ -111,13 +199,16 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
     const int nP = Mp >> 5;
     const double inv_lamz = 1.0 / lamz;
     const double diag = inv_lamz + diag_add;
+    double* __restrict__ D = sm.D;
+    double* __restrict__ LT = sm.LT;
 
     __syncthreads();   // previous user of the shared buffers is done
     for (int idx = tid; idx < Mp * d; idx += NT) {
-        int r = idx / d, k = idx - r * d;
-        sm.S[idx] = (r < m) ? X[(size_t)r * d + k] * sqrt(beta[k]) : 0.0;
+        int k = idx / Mp, r = idx - k * Mp;
+        sm.ST[idx] = (r < m) ? X[(size_t)r * d + k] * sqrt(beta[k]) : 0.0;
     }
     for (int r = tid; r < Mp; r += NT) sm.wres[r] = (r < m) ? w[r] : 0.0;
+    fill_exp_table(sm.etab);
     if (tid == 0) sm.flag[0] = 0;
     double logdet = 0.0, quad = 0.0;    // partial sums, live in warp 0
     __syncthreads();
@@ -126,175 +217,185 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         const int row0 = j << 5;
         const int Rj = Mp - row0;
         double* __restrict__ Lpj = Lp + panel_off(j, Mp);
-        const int npass = (Rj + PASS_ROWS - 1) / PASS_ROWS;
+        const int nunits = Rj >> 3;
+        // this warp owns units u = warp + NWARP*t (t = 0, 1, ...), processed two at a time; units 0..3 are the
+        // diagonal block (t = 0 of warps 0..3)
+        const int nmy = (nunits - warp + NWARP - 1) / NWARP;
 
-        for (int ps = 0; ps < npass; ++ps) {
-            const int r_lo = row0 + ps * PASS_ROWS;
-            const int r_hi = min(Mp, r_lo + PASS_ROWS);
-            const int nrows = r_hi - r_lo;
-            const int nun = nrows >> 3;
-
-            // ------------------------------------------------------------------ 1. DMMA update
-            double acc[4][4][2];
+        // GEMM + covariance of the pair of units starting at t0: p = C - S in the accumulator layout
+        auto make_pair = [&](int t0, double (&acc)[2][4][2], int (&rb)[2]) -> int {
+            const int nu = min(2, nmy - t0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i) {
+                rb[i] = row0 + 8 * (warp + NWARP * (t0 + ((i < nu) ? i : 0)));
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
+            }
+            if (j > 0) {
+                if (nu == 2) panel_gemm<2>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0);
+                else if (nu == 1) panel_gemm<1>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (i < nu)
+                    unit_cov(acc[i], sm.ST, Mp, rb[i] + g, rb[i] + g < m, sm.ST, Mp, d, m, row0, q, inv_lamz, diag,
+                             true, sm.etab);
+            return nu;
+        };
+        // X = P Minv^T for one unit, store to the packed factor, update the running forward solve of w
+        auto finish_unit = [&](const double (&pu)[4][2], int rbase) {
+            double xt[4][2];
+            unit_trsm(pu, xt, sm.Minv, g, q);
+            const int r = rbase + g;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const double2 u2 = *reinterpret_cast<const double2*>(sm.uj + 8 * cb + 2 * q);
+                s0 = fma(xt[cb][0], u2.x, s0);
+                s1 = fma(xt[cb][1], u2.y, s1);
+                *reinterpret_cast<double2*>(Lpj + (long long)cb * Rj * 8 + (long long)(r - row0) * 8 + 2 * q) =
+                    make_double2(xt[cb][0], xt[cb][1]);
+            }
+            double s = s0 + s1;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0) sm.wres[r] -= s;
+        };
 
-            bool act[4];
-            int rb[4];
+        // ---------------------------------------------------------------------- first pair (held across the
+        // diagonal-block phase in registers)
+        double acc0[2][4][2];
+        int rb0[2];
+        const int nu0 = make_pair(0, acc0, rb0);
+        if (warp < 4) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int u = warp + NWARP * i;
-                act[i] = u < nun;
-                rb[i] = r_lo + 8 * (act[i] ? u : 0);
-            }
-
-            if (act[0] && j > 0) {
-                const int nmine = (nun - warp + NWARP - 1) / NWARP;     // units owned by this warp (1..4)
-                switch (nmine) {
-                    case 1: panel_gemm<1>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
-                    case 2: panel_gemm<2>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
-                    case 3: panel_gemm<3>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
-                    default: panel_gemm<4>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0); break;
-                }
-            }
-
-            // ------------------------------------------------------------------ 2. covariance, P = C - S
+            for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (act[i]) {
-                    const int r = rb[i] + g;
-                    const double* Sr = sm.S + (size_t)r * d;
-#pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int c = row0 + 8 * cb + 2 * q + e;
-                            double v;
-                            if (r == c) {
-                                v = (r < m) ? diag : 1.0;
-                            } else if (r < m && c < m) {
-                                const double* Sc = sm.S + (size_t)c * d;
-                                double dist = 0.0;
-                                for (int k = 0; k < d; ++k) {
-                                    double t = Sr[k] - Sc[k];
-                                    dist = fma(t, t, dist);
-                                }
-                                v = exp(-dist) * inv_lamz;
-                            } else {
-                                v = 0.0;
-                            }
-                            sm.Ps[(r - r_lo) * PS_LD + (c - row0)] = v - acc[i][cb][e];
-                        }
-                    }
-                }
-            }
-            __syncthreads();                                                     // #1
-
-            // ------------------------------------------------------------------ 3. diagonal block
-            if (ps == 0) {
-                if (warp == 0) {
-                    double x[32];
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) x[c] = sm.Ps[lane * PS_LD + c];
-                    double mypiv = 1.0;
-                    bool ok = true;
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        if (ok) {
-                            const double dk = __shfl_sync(0xffffffffu, x[k], k);
-                            if (!(dk > 0.0) || !(dk < 1.0e300)) {
-                                ok = false;
-                                if (lane == 0) sm.flag[0] = row0 + k + 1;
-                            } else {
-                                if (lane == k) mypiv = dk;
-                                const double rk = rsqrt(dk);
-                                double lik = x[k] * rk;
-                                if (lane == k) lik = dk * rk;
-                                x[k] = lik;
-                                sm.LT[k * LT_LD + lane] = (lane >= k) ? lik : 0.0;
-                                if (lane == 0) sm.rdiag[k] = rk;
-                                __syncwarp();
-#pragma unroll
-                                for (int c = k + 1; c < 32; ++c) x[c] = fma(-lik, sm.LT[k * LT_LD + c], x[c]);
-                            }
-                        }
-                    }
-                    if (ok) logdet += 0.5 * log(mypiv);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) sm.Ps[lane * PS_LD + c] = (c > lane) ? 0.0 : x[c];
-                }
-                __syncthreads();                                                 // #2
-                if (sm.flag[0] != 0) {
-                    if (tid == 0 && info) *info = sm.flag[0];
-                    return -INFINITY;
-                }
-            }
-
-            // ------------------------------------------------------------------ 4. TRSM rows / forward solve of w
-            const bool isdiag = (ps == 0) && (tid < 32);
-            const bool myrow = tid < nrows;
-            double x[32];                   // row of the panel owned by this thread
-            if (myrow) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) x[c] = sm.Ps[tid * PS_LD + c];
-            } else {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) x[c] = 0.0;
-            }
-            if (isdiag) {
-                double b = sm.wres[row0 + lane];
-                double myu = 0.0;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
-                    if (lane == c) myu = uc;
-                    if (lane > c) b = fma(-x[c], uc, b);
-                }
-                sm.uj[lane] = myu;
-                quad += myu * myu;
-                if (u_out) u_out[row0 + lane] = myu;
-            } else if (myrow) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const double xc = x[c] * sm.rdiag[c];
-                    x[c] = xc;
-                    const double* lt = sm.LT + c * LT_LD;
-                    if (((c + 1) & 1) && c + 1 < 32) x[c + 1] = fma(-xc, lt[c + 1], x[c + 1]);
-#pragma unroll
-                    for (int cp = (c + 2) & ~1; cp < 32; cp += 2) {
-                        const double2 l2 = *reinterpret_cast<const double2*>(lt + cp);
-                        x[cp] = fma(-xc, l2.x, x[cp]);
-                        x[cp + 1] = fma(-xc, l2.y, x[cp + 1]);
-                    }
-                }
-            }
-            __syncthreads();                                                     // #3
-
-            // ------------------------------------------------------------------ 5. store panel rows, update w
-            if (myrow) {
-                const int r = r_lo + tid;
-                if (!isdiag) {
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 32; c += 2) {
-                        const double2 u2 = *reinterpret_cast<const double2*>(sm.uj + c);
-                        s0 = fma(x[c], u2.x, s0);
-                        s1 = fma(x[c + 1], u2.y, s1);
-                    }
-                    sm.wres[r] -= (s0 + s1);
-                }
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    double* dst = Lpj + (long long)ks * Rj * 8 + (long long)(r - row0) * 8;
-#pragma unroll
-                    for (int c = 0; c < 8; c += 2)
-                        *reinterpret_cast<double2*>(dst + c) = make_double2(x[8 * ks + c], x[8 * ks + c + 1]);
-                }
-            }
-            __syncthreads();                                                     // #4
+                for (int e = 0; e < 2; ++e)
+                    D[(8 * warp + g) * D_LD + 8 * cb + 2 * q + e] = acc0[0][cb][e];
         }
+        __syncthreads();                                                         // (A)
+        if (warp == 0) {
+            // Cholesky of the 32x32 block, lane = row.  Columns are processed in blocks of 8 held in registers
+            // (pivots and multipliers move by shuffle); the trailing columns get one rank-8 update per block
+            // from shared memory instead of one read-modify-write per pivot.
+            double mypiv = 1.0;
+            int bad = 0;
+#pragma unroll 1
+            for (int k0 = 0; k0 < 32 && !bad; k0 += 8) {
+                double x[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) x[kk] = D[lane * D_LD + k0 + kk];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int k = k0 + kk;
+                    const double dk = __shfl_sync(0xffffffffu, x[kk], k);
+                    if (!(dk > 0.0) || !(dk < 1.0e300)) { if (!bad) bad = row0 + k + 1; }
+                    const double rk = rsqrt(dk);
+                    const double lik = (lane == k) ? dk * rk : x[kk] * rk;
+                    if (lane == k) mypiv = dk;
+                    x[kk] = lik;
+                    if (lane == 0) sm.rdiag[k] = rk;
+#pragma unroll
+                    for (int k2 = kk + 1; k2 < 8; ++k2)
+                        x[k2] = fma(-lik, __shfl_sync(0xffffffffu, lik, k0 + k2), x[k2]);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const bool low = lane >= k0 + kk;
+                    D[lane * D_LD + k0 + kk] = low ? x[kk] : 0.0;
+                    LT[(k0 + kk) * LT_LD + lane] = low ? x[kk] : 0.0;
+                }
+                __syncwarp();
+#pragma unroll 2
+                for (int c = k0 + 8; c < 32; ++c) {
+                    double a = D[lane * D_LD + c];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) a = fma(-x[kk], LT[(k0 + kk) * LT_LD + c], a);
+                    D[lane * D_LD + c] = a;
+                }
+                __syncwarp();
+            }
+            if (bad) { if (lane == 0) sm.flag[0] = bad; }
+            else logdet += 0.5 * log(mypiv);
+        }
+        __syncthreads();                                                         // (B0)
+        if (sm.flag[0] != 0) {
+            if (tid == 0 && info) *info = sm.flag[0];
+            return -INFINITY;
+        }
+        if (warp == 0) {
+            // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]
+            double b = sm.wres[row0 + lane];
+            double myu = 0.0;
+#pragma unroll 1
+            for (int c = 0; c < 32; ++c) {
+                const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
+                if (lane == c) myu = uc;
+                if (lane > c) b = fma(-D[lane * D_LD + c], uc, b);
+            }
+            sm.uj[lane] = myu;
+            quad += myu * myu;
+            if (u_out) u_out[row0 + lane] = myu;
+            // store the diagonal rows of L (zeros above the diagonal)
+#pragma unroll 1
+            for (int ks = 0; ks < 4; ++ks) {
+                double* dst = Lpj + (long long)ks * Rj * 8 + (long long)lane * 8;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    const int cc = 8 * ks + c;
+                    *reinterpret_cast<double2*>(dst + c) =
+                        make_double2(cc > lane ? 0.0 : D[lane * D_LD + cc], cc + 1 > lane ? 0.0 : D[lane * D_LD + cc + 1]);
+                }
+            }
+        } else if (warp == 1) {
+            // Minv = Ljj^-1: lane k solves Ljj y = e_k.  Rows in blocks of 8: the contribution of all earlier
+            // rows is accumulated for the 8 rows at once (one own-column load + four broadcast LDS.128 of
+            // LT[t][i0..i0+7] per t), then an 8x8 triangular solve in registers.
+            double* gm = Lp + minv_off(Mp) + 1024LL * j;
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+                double y[8];
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii) y[ii] = (i0 + ii == lane) ? 1.0 : 0.0;
+#pragma unroll 2
+                for (int t = 0; t < i0; ++t) {
+                    const double yt = sm.Minv[t * MI_LD + lane];
+                    const double* lt = LT + t * LT_LD + i0;              // L[i0+ii][t]
+#pragma unroll
+                    for (int ii = 0; ii < 8; ii += 2) {
+                        const double2 l2 = *reinterpret_cast<const double2*>(lt + ii);
+                        y[ii] = fma(-l2.x, yt, y[ii]);
+                        y[ii + 1] = fma(-l2.y, yt, y[ii + 1]);
+                    }
+                }
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii) {
+                    y[ii] *= sm.rdiag[i0 + ii];
+#pragma unroll
+                    for (int i2 = ii + 1; i2 < 8; ++i2) y[i2] = fma(-LT[(i0 + ii) * LT_LD + i0 + i2], y[ii], y[i2]);
+                }
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii) {
+                    sm.Minv[(i0 + ii) * MI_LD + lane] = y[ii];          // Minv[i][k = lane]
+                    gm[(i0 + ii) * 32 + lane] = y[ii];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();                                                         // (B)
+
+        // ---------------------------------------------------------------------- finish the held pair, then the rest
+        if (nu0 >= 1 && warp >= 4) finish_unit(acc0[0], rb0[0]);     // t = 0 of warps 0..3 is the diagonal block
+        if (nu0 >= 2) finish_unit(acc0[1], rb0[1]);
+        for (int t0 = 2; t0 < nmy; t0 += 2) {
+            double acc[2][4][2];
+            int rb[2];
+            const int nu = make_pair(t0, acc, rb);
+            finish_unit(acc[0], rb[0]);
+            if (nu >= 2) finish_unit(acc[1], rb[1]);
+        }
+        __syncthreads();                                                         // (C)
     }
 
     if (warp == 0) {

@@ -29,9 +29,12 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 constexpr int NB = 32;          // panel width of the blocked factorisation
-constexpr int NT = 512;         // threads per CTA of the fused kernels
+constexpr int NT = 256;         // threads per CTA of the fused kernels (two CTAs share an SM)
 constexpr int NWARP = NT / 32;
-constexpr int PASS_ROWS = 512;  // rows handled per pass (one TRSM row per thread)
+constexpr int PASS_UNITS = 4 * NWARP;      // 8-row units per pass (4 per warp: 64 accumulator registers)
+constexpr int PASS_ROWS = 8 * PASS_UNITS;  // rows handled per pass
+constexpr int D_LD = 33;        // staging of the 32x32 diagonal block
+constexpr int MI_LD = 40;       // leading dimension of the inverted diagonal block (conflict-free LDS.128)
 constexpr int PS_LD = 33;       // leading dimension of the panel staging buffer (odd: conflict-free rows)
 constexpr int LT_LD = 34;       // leading dimension of the transposed diagonal factor (even: 16 B pairs)
 
@@ -43,9 +46,11 @@ __host__ __device__ inline int round_up32(int m) { return (m + 31) & ~31; }
 __host__ __device__ inline long long panel_off(int kb, int Mp) {
     return 32LL * ((long long)kb * Mp - 16LL * kb * (kb - 1));
 }
+// after the panels: nP inverted diagonal blocks, [nP][32][32] row-major (Minv[c][k] = (Ljj^-1)[c][k])
+__host__ __device__ inline long long minv_off(int Mp) { return panel_off(Mp / 32, Mp); }
 __host__ __device__ inline long long packed_doubles(int Mp) {
     int nP = Mp / 32;
-    return panel_off(nP, Mp);
+    return panel_off(nP, Mp) + 1024LL * nP;
 }
 
 // FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8).  SASS: DMMA.8x8x4

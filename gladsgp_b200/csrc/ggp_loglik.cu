@@ -127,7 +127,7 @@ cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // (2) batched fused log-likelihood: one CTA per matrix.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 3)
 loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const double* __restrict__ W,
                       long long w_stride, const double* __restrict__ beta, const double* __restrict__ lamz,
                       const double* __restrict__ diag_add, double* __restrict__ Lws, long long l_stride,
@@ -159,6 +159,15 @@ __global__ void unpack_factor_kernel(const double* __restrict__ Lws, long long l
         }
         out[idx] = v;
     }
+}
+
+// test hook for the in-kernel exponential
+__global__ void exp_neg_kernel(const double* __restrict__ y, double* __restrict__ out, int n)
+{
+    __shared__ double etab[32];
+    fill_exp_table(etab);
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = exp_neg(y[i], etab);
 }
 
 }  // namespace ggp
@@ -194,6 +203,14 @@ int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, co
     GGP_CUDA(cudaFuncSetAttribute(cross_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + CT - 1) / CT, (m + CT - 1) / CT, B);
     cross_cov_kernel<<<grid, 256, smem, st>>>(X, m, Xp, n, d, beta, lamz, S21_out);
+    GGP_CUDA(cudaGetLastError());
+    return GGP_OK;
+}
+
+int ggp_debug_exp_neg_f64(const double* y, double* out, int n, void* stream)
+{
+    GGP_ARG(y && out && n > 0, "bad argument");
+    exp_neg_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(y, out, n);
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }

@@ -114,7 +114,7 @@ __device__ inline void gather_block_params(const ggp_mcmc_args& a, const double*
     diag_add = 1.0 / (a.lamsim[j] * lamwos) + 1.0 / lamws;
 }
 
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 3)
 sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, int t)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,7 +161,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
 }
 
 // mode 0: sigwl <- per-PC terms of the current state.  mode 1: sigwl_cand <- terms under candidate lamWOs.
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 3)
 eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride,
                 double* __restrict__ sig_cand, int mode)
 {

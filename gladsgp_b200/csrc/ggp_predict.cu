@@ -90,10 +90,11 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
             if (j > 0) {
-                int rb[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) rb[i] = 8 * (warp + NWARP * i);
-                panel_gemm<4>(acc, Vw, Lp, Mp, j, row0, rb, g, q, PB);
+                for (int h = 0; h < 2; ++h) {
+                    int rb[2] = {8 * (warp + NWARP * (2 * h)), 8 * (warp + NWARP * (2 * h + 1))};
+                    panel_gemm<2>(*reinterpret_cast<double (*)[2][4][2]>(&acc[2 * h]), Vw, Lp, Mp, j, row0, rb, g, q, PB);
+                }
             }
             // ---- 2. cross-covariance entries, P = S21^T - S
 #pragma unroll

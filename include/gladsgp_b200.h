@@ -50,6 +50,8 @@ int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, co
  * W: vector b starts at W + b*w_stride.  factor_ws[B][ggp_factor_doubles(m)] receives the packed
  * factor (layout in DESIGN.md; unpack with ggp_factor_unpack_f64).  u_out (nullable)
  * [B][ggp_padded_m(m)] receives L^-1 W[b], zero padded.  info_out nullable. */
+/* test hook: out[i] = exp(y[i]) for y <= 0 with the kernel-internal exponential (about 1 ulp) */
+int ggp_debug_exp_neg_f64(const double* y, double* out, int n, void* stream);
 long long ggp_factor_doubles(int m);
 int ggp_padded_m(int m);
 int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long long w_stride,

@@ -130,3 +130,19 @@ def test_mcmc_uniform_stream_matches_oracle(cuda):
     acc_ref = np.array([tr['accept'] for tr in mod.trace], dtype=np.uint8).reshape(n_steps, 1, P)
     assert np.array_equal(out['accepted'].cpu().numpy(), acc_ref)
     np.testing.assert_allclose(out['draws'].cpu().numpy()[:, 0, :], ref_draws, rtol=1e-12)
+
+
+def test_in_kernel_exponential_accuracy(cuda):
+    """The fused kernels use their own exp for y <= 0 (table + degree-7 polynomial): ~1 ulp."""
+    import torch
+    from gladsgp_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    y = -np.concatenate([rng.uniform(0, 1e-3, 20000), rng.uniform(0, 5, 50000), rng.uniform(5, 680, 30000), [0.0]])
+    yd = torch.as_tensor(y, device='cuda'); out = torch.empty_like(yd)
+    _lib.check(lib.ggp_debug_exp_neg_f64(_lib.ptr(yd), _lib.ptr(out), y.size, _lib.stream_ptr()))
+    got = out.cpu().numpy()
+    ref = np.exp(y)
+    rel = np.abs(got - ref) / ref
+    assert rel.max() < 4.5e-16, rel.max()
+    assert got[-1] == 1.0

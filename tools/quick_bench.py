@@ -41,7 +41,7 @@ def main():
     t = synthetic.design(m, q)
     X = np.concatenate([0.5 * np.ones((m, 1)), t.astype(np.float64)], axis=1)
     rng = np.random.default_rng(0)
-    for B in (1, 10, 148, 296, 592):
+    for B in (1, 10, 148, 296, 444, 888):
         beta = np.exp(rng.uniform(np.log(0.05), np.log(3.0), size=(B, d)))
         lamz = rng.uniform(0.5, 2.0, B); dadd = rng.uniform(1e-3, 1e-2, B)
         W = rng.standard_normal((B, m))
