@@ -26,6 +26,31 @@
 
 namespace ggp {
 
+// optional phase timing (developer diagnostics): cycles spent by warp 0 and warp 7 of block 0 in each phase
+#ifdef GGP_PHASES
+__device__ unsigned long long g_phase[32];
+#define GGP_TICK(slot)                                                                      \
+    do {                                                                                    \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 7)) {  \
+            unsigned long long now__ = clock64();                                           \
+            g_phase[(warp == 0 ? 0 : 16) + (slot)] += now__ - tlast__;                      \
+            tlast__ = now__;                                                                \
+        }                                                                                   \
+    } while (0)
+#define GGP_TICKW(w, slot, dep)                                                             \
+    do {                                                                                    \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && warp == (w)) {                            \
+            unsigned long long now__ = clock64();                                           \
+            if ((dep) == 1.2345e300) now__ = 0;                                             \
+            if (lane == 0) { g_phase[(slot)] += now__ - tserial__; }                        \
+            tserial__ = now__;                                                              \
+        }                                                                                   \
+    } while (0)
+#else
+#define GGP_TICK(slot) do { } while (0)
+#define GGP_TICKW(w, slot, dep) do { } while (0)
+#endif
+
 struct EvalSmem {
     double* D;      // [32][D_LD]   diagonal block: P on entry, rows of Ljj after the factorisation
     double* LT;     // [32][LT_LD]  LT[k][i] = L[i][k]
@@ -35,12 +60,22 @@ struct EvalSmem {
     double* red;    // [8]
     double* etab;   // [32] 2^(j/32)
     double* wres;   // [Mp]
-    double* ST;     // [d][Mp] sqrt(beta)-scaled coordinates, transposed
+    double* sb;     // [d]     sqrt(beta)
+    double* SC;     // [d][32] sqrt(beta)-scaled coordinates of the current panel's columns
     int* flag;      // [4]
+    int* soff;      // [4*nP] offset (doubles) of sub-slab s = 4*kb + ks such that soff[s] + r*8 + c addresses row r
 };
 
 __host__ __device__ inline size_t eval_smem_bytes(int Mp, int d) {
-    return (size_t)(32 * D_LD + 32 * LT_LD + 32 * MI_LD + 32 + 32 + 8 + 32 + Mp + (size_t)Mp * d) * sizeof(double) + 16;
+    return (size_t)(32 * D_LD + 32 * LT_LD + 32 * MI_LD + 32 + 32 + 8 + 32 + Mp + (size_t)33 * ((d + 1) & ~1)) * sizeof(double) + 16 + (size_t)(Mp / 8) * sizeof(int);
+}
+
+// shared-memory carve-out (percent of 228 KB) that just fits three CTAs: the rest stays L1 so that the
+// B-operand rows of a panel, shared by the eight warps, are served from L1 instead of L2
+inline int eval_carveout_pct(size_t smem) {
+    size_t need = GGP_CTAS_PER_SM * (smem + 1024);
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    return pct > 100 ? 100 : pct;
 }
 
 __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
@@ -53,9 +88,11 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     s.red = p;      p += 8;
     s.etab = p;     p += 32;
     s.wres = p;     p += Mp;
-    s.ST = p;       p += (size_t)Mp * d;
+    s.SC = p;       p += (size_t)32 * ((d + 1) & ~1);
+    s.sb = p;       p += ((d + 1) & ~1);
     s.D = p;        p += 32 * D_LD;
     s.flag = reinterpret_cast<int*>(p);
+    s.soff = s.flag + 4;
     return s;
 }
 
@@ -88,33 +125,45 @@ __device__ inline void fill_exp_table(double* etab)
     if (threadIdx.x < 32) etab[threadIdx.x] = exp2((double)threadIdx.x * 0.03125);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ inline void fill_slab_offsets(int* soff, int Mp)
+{
+    for (int s = threadIdx.x; s < Mp / 8; s += blockDim.x) {
+        const int kb = s >> 2, ks = s & 3;
+        soff[s] = (int)(panel_off(kb, Mp) + (long long)ks * (Mp - 32 * kb) * 8 - 32LL * kb * 8);
+    }
+}
+
 // S += A[rows, 0:32j] * Lb[panel rows, 0:32j]^T for NU 8-row units of one warp (DMMA.8x8x4).
 // A-operand rows come from `Ap` (packed factor layout when a_ld == 0, else a [slab][a_ld][8] layout
 // indexed by local row), B-operand rows from the packed factor `Lb`.  NU is a template parameter so
 // that no predicated-off DMMA is ever issued (a predicated-off DMMA still occupies the pipe).
+// Latency: the A fragment of the next sub-slab is loaded one iteration ahead into registers; further
+// ahead, lanes 0..4NU-1 pull the A lines of sub-slab s+6 into L2 and lanes 16..31 the B lines of
+// sub-slab s+2 into L1 (the B rows are shared by all warps of the CTA).
 template <int NU>
 static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const double* __restrict__ Ap,
-                                                  const double* __restrict__ Lb, int Mp, int j, int row0,
-                                                  const int (&rb)[2], int g, int q, int a_ld)
+                                                  const double* __restrict__ Lb, const int* __restrict__ soff, int j,
+                                                  int row0, const int (&rb)[2], int g, int q, int a_ld)
 {
+    constexpr int PDA = 6, PDB = 2;
     const int nsl = 4 * j;
-    auto a_slab = [&](int s) -> const double* {
-        if (a_ld) return Ap + (size_t)s * a_ld * 8;
-        int kb = s >> 2, ks = s & 3;
-        return Ap + panel_off(kb, Mp) + (long long)ks * (Mp - 32 * kb) * 8 - 32LL * kb * 8;
-    };
-    auto b_slab = [&](int s) -> const double* {
-        int kb = s >> 2, ks = s & 3;
-        return Lb + panel_off(kb, Mp) + (long long)ks * (Mp - 32 * kb) * 8 - 32LL * kb * 8;
-    };
+    const int lane = 4 * g + q;
+    auto a_slab = [&](int s) -> const double* { return a_ld ? Ap + (size_t)s * a_ld * 8 : Ap + soff[s]; };
     double2 an[NU];
     {
         const double* sl = a_slab(0);
 #pragma unroll
         for (int i = 0; i < NU; ++i) an[i] = ldcg2(sl + (rb[i] + g) * 8 + 2 * q);
     }
+    // prefetch roles
+    const int pf_unit = (lane >> 2) < NU ? (lane >> 2) : 0;
+    const int pf_arow = rb[pf_unit] * 8 + (lane & 3) * 16;          // A: 4 lines of 128 B per unit
+    const int pf_brow = (row0 + 2 * (lane & 15)) * 8;               // B: 16 lines of 128 B per sub-slab
     for (int s = 0; s < nsl; ++s) {
-        const double* sl = b_slab(s);
+        const double* sl = Lb + soff[s];
         double2 a[NU];
 #pragma unroll
         for (int i = 0; i < NU; ++i) a[i] = an[i];
@@ -123,6 +172,8 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
 #pragma unroll
             for (int i = 0; i < NU; ++i) an[i] = ldcg2(sn + (rb[i] + g) * 8 + 2 * q);
         }
+        if (lane < 4 * NU) { if (s + PDA < nsl) prefetch_l2(a_slab(s + PDA) + pf_arow); }
+        else if (lane >= 16) { if (s + PDB < nsl) prefetch_l1(Lb + soff[s + PDB] + pf_brow); }
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
             const double2 b = *reinterpret_cast<const double2*>(sl + (row0 + 8 * cb + g) * 8 + 2 * q);
@@ -152,19 +203,21 @@ static __device__ __forceinline__ void unit_trsm(const double (&p)[4][2], double
 }
 
 // Covariance entries of one unit (8 rows x 32 panel columns) in the accumulator layout: p = C - p.
-// row_is_train: rows index training points (self covariance, with diagonal / padding rules);
-// otherwise rows index a separate coordinate array (cross covariance) and `nrow_valid` masks padding.
-static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double* __restrict__ RT, int rld, int r,
-                                                bool row_ok, const double* __restrict__ ST, int Mp, int d, int m,
-                                                int row0, int q, double inv_lamz, double diag, bool self,
+// Row coordinates come from global memory (Xr[r][d], L1/L2 resident) and are scaled by sqrt(beta) on the
+// fly -- the same expression that fills SC, so the two sides round identically; column coordinates of the
+// panel sit in shared memory (SC[k][32]).  self: rows are training points (diagonal / padding rules).
+static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double* __restrict__ Xr, int r, bool row_ok,
+                                                const double* __restrict__ SC, const double* __restrict__ sb, int d,
+                                                int m, int row0, int q, double inv_lamz, double diag, bool self,
                                                 const double* __restrict__ etab)
 {
     double dist[4][2];
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) { dist[cb][0] = 0.0; dist[cb][1] = 0.0; }
+    const double* xr = Xr + (size_t)(row_ok ? r : 0) * d;
     for (int k = 0; k < d; ++k) {
-        const double sr = RT[(size_t)k * rld + r];
-        const double* sc = ST + (size_t)k * Mp + row0 + 2 * q;
+        const double sr = __ldg(xr + k) * sb[k];
+        const double* sc = SC + k * 32 + 2 * q;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
             const double2 c2 = *reinterpret_cast<const double2*>(sc + 8 * cb);
@@ -182,6 +235,16 @@ static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double*
             if (self && r == c) v = (r < m) ? diag : 1.0;
             p[cb][e] = v - p[cb][e];
         }
+    }
+}
+
+// scaled coordinates of the 32 columns of panel `row0` -> SC[k][32]; all threads, caller syncs
+static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SC, const double* __restrict__ X,
+                                                         const double* __restrict__ sb, int d, int m, int row0)
+{
+    for (int idx = threadIdx.x; idx < 32 * d; idx += blockDim.x) {
+        const int k = idx >> 5, c = idx & 31;
+        SC[idx] = (row0 + c < m) ? __ldg(X + (size_t)(row0 + c) * d + k) * sb[k] : 0.0;
     }
 }
 
@@ -203,15 +266,17 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
     double* __restrict__ LT = sm.LT;
 
     __syncthreads();   // previous user of the shared buffers is done
-    for (int idx = tid; idx < Mp * d; idx += NT) {
-        int k = idx / Mp, r = idx - k * Mp;
-        sm.ST[idx] = (r < m) ? X[(size_t)r * d + k] * sqrt(beta[k]) : 0.0;
-    }
+    if (tid < d) sm.sb[tid] = sqrt(beta[tid]);
     for (int r = tid; r < Mp; r += NT) sm.wres[r] = (r < m) ? w[r] : 0.0;
     fill_exp_table(sm.etab);
+    fill_slab_offsets(sm.soff, Mp);
     if (tid == 0) sm.flag[0] = 0;
     double logdet = 0.0, quad = 0.0;    // partial sums, live in warp 0
     __syncthreads();
+#ifdef GGP_PHASES
+    unsigned long long tlast__ = clock64();
+    unsigned long long tserial__ = 0;
+#endif
 
     for (int j = 0; j < nP; ++j) {
         const int row0 = j << 5;
@@ -221,6 +286,9 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         // this warp owns units u = warp + NWARP*t (t = 0, 1, ...), processed two at a time; units 0..3 are the
         // diagonal block (t = 0 of warps 0..3)
         const int nmy = (nunits - warp + NWARP - 1) / NWARP;
+        fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
+        __syncthreads();
+        GGP_TICK(0);
 
         // GEMM + covariance of the pair of units starting at t0: p = C - S in the accumulator layout
         auto make_pair = [&](int t0, double (&acc)[2][4][2], int (&rb)[2]) -> int {
@@ -232,14 +300,14 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                 for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
             }
             if (j > 0) {
-                if (nu == 2) panel_gemm<2>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0);
-                else if (nu == 1) panel_gemm<1>(acc, Lp, Lp, Mp, j, row0, rb, g, q, 0);
+                if (nu == 2) panel_gemm<2>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
+                else if (nu == 1) panel_gemm<1>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i)
                 if (i < nu)
-                    unit_cov(acc[i], sm.ST, Mp, rb[i] + g, rb[i] + g < m, sm.ST, Mp, d, m, row0, q, inv_lamz, diag,
-                             true, sm.etab);
+                    unit_cov(acc[i], X, rb[i] + g, rb[i] + g < m, sm.SC, sm.sb, d, m, row0, q, inv_lamz, diag, true,
+                             sm.etab);
             return nu;
         };
         // X = P Minv^T for one unit, store to the packed factor, update the running forward solve of w
@@ -267,6 +335,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         double acc0[2][4][2];
         int rb0[2];
         const int nu0 = make_pair(0, acc0, rb0);
+        GGP_TICK(1);
         if (warp < 4) {
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
@@ -275,12 +344,14 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                     D[(8 * warp + g) * D_LD + 8 * cb + 2 * q + e] = acc0[0][cb][e];
         }
         __syncthreads();                                                         // (A)
+        GGP_TICK(2);
         if (warp == 0) {
             // Cholesky of the 32x32 block, lane = row.  Columns are processed in blocks of 8 held in registers
             // (pivots and multipliers move by shuffle); the trailing columns get one rank-8 update per block
             // from shared memory instead of one read-modify-write per pivot.
             double mypiv = 1.0;
             int bad = 0;
+            GGP_TICKW(0, 9, D[lane * D_LD]);      // (slot 9: everything up to the start of the factorisation)
 #pragma unroll 1
             for (int k0 = 0; k0 < 32 && !bad; k0 += 8) {
                 double x[8];
@@ -316,10 +387,13 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                 }
                 __syncwarp();
             }
+            GGP_TICKW(0, 10, D[lane * D_LD + 31]);  // slot 10: factorisation
             if (bad) { if (lane == 0) sm.flag[0] = bad; }
             else logdet += 0.5 * log(mypiv);
         }
+        GGP_TICK(3);
         __syncthreads();                                                         // (B0)
+        GGP_TICK(4);
         if (sm.flag[0] != 0) {
             if (tid == 0 && info) *info = sm.flag[0];
             return -INFINITY;
@@ -327,6 +401,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         if (warp == 0) {
             // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]
             double b = sm.wres[row0 + lane];
+            GGP_TICKW(0, 11, b);                    // slot 11: factor end -> usolve start (barrier B0)
             double myu = 0.0;
 #pragma unroll 1
             for (int c = 0; c < 32; ++c) {
@@ -348,7 +423,9 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                         make_double2(cc > lane ? 0.0 : D[lane * D_LD + cc], cc + 1 > lane ? 0.0 : D[lane * D_LD + cc + 1]);
                 }
             }
+            GGP_TICKW(0, 12, quad);                 // slot 12: usolve + diagonal row store
         } else if (warp == 1) {
+            GGP_TICKW(1, 13, sm.rdiag[0]);          // slot 13: everything else for warp 1
             // Minv = Ljj^-1: lane k solves Ljj y = e_k.  Rows in blocks of 8: the contribution of all earlier
             // rows is accumulated for the 8 rows at once (one own-column load + four broadcast LDS.128 of
             // LT[t][i0..i0+7] per t), then an 8x8 triangular solve in registers.
@@ -382,8 +459,11 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                 }
                 __syncwarp();
             }
+            GGP_TICKW(1, 14, sm.Minv[lane]);        // slot 14: Minv
         }
+        GGP_TICK(5);
         __syncthreads();                                                         // (B)
+        GGP_TICK(6);
 
         // ---------------------------------------------------------------------- finish the held pair, then the rest
         if (nu0 >= 1 && warp >= 4) finish_unit(acc0[0], rb0[0]);     // t = 0 of warps 0..3 is the diagonal block
@@ -395,7 +475,9 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
             finish_unit(acc[0], rb[0]);
             if (nu >= 2) finish_unit(acc[1], rb[1]);
         }
+        GGP_TICK(7);
         __syncthreads();                                                         // (C)
+        GGP_TICK(8);
     }
 
     if (warp == 0) {

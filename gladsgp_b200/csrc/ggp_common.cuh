@@ -31,6 +31,9 @@ int cuda_fail(cudaError_t e, const char* what);
 constexpr int NB = 32;          // panel width of the blocked factorisation
 constexpr int NT = 256;         // threads per CTA of the fused kernels (two CTAs share an SM)
 constexpr int NWARP = NT / 32;
+#ifndef GGP_CTAS_PER_SM
+#define GGP_CTAS_PER_SM 3     // register budget of the fused kernels: 65536 / (256 * CTAs)
+#endif
 constexpr int PASS_UNITS = 4 * NWARP;      // 8-row units per pass (4 per warp: 64 accumulator registers)
 constexpr int PASS_ROWS = 8 * PASS_UNITS;  // rows handled per pass
 constexpr int D_LD = 33;        // staging of the 32x32 diagonal block

@@ -127,7 +127,7 @@ cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // (2) batched fused log-likelihood: one CTA per matrix.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const double* __restrict__ W,
                       long long w_stride, const double* __restrict__ beta, const double* __restrict__ lamz,
                       const double* __restrict__ diag_add, double* __restrict__ Lws, long long l_stride,
@@ -207,6 +207,17 @@ int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, co
     return GGP_OK;
 }
 
+#ifdef GGP_PHASES
+int ggp_debug_phase_cycles(unsigned long long* out_host, int reset)
+{
+    unsigned long long z[32] = {0};
+    GGP_CUDA(cudaDeviceSynchronize());
+    GGP_CUDA(cudaMemcpyFromSymbol(out_host, ggp::g_phase, sizeof(z)));
+    if (reset) GGP_CUDA(cudaMemcpyToSymbol(ggp::g_phase, z, sizeof(z)));
+    return GGP_OK;
+}
+#endif
+
 int ggp_debug_exp_neg_f64(const double* y, double* out, int n, void* stream)
 {
     GGP_ARG(y && out && n > 0, "bad argument");
@@ -233,6 +244,7 @@ int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long 
     }
     cudaStream_t st = (cudaStream_t)stream;
     GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
     loglik_batched_kernel<<<B, NT, smem, st>>>(X, m, Mp, d, W, w_stride, beta, lamz, diag_add, factor_ws,
                                                packed_doubles(Mp), u_out, loglik_out, info_out);
     GGP_CUDA(cudaGetLastError());

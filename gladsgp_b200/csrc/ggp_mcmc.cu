@@ -114,7 +114,7 @@ __device__ inline void gather_block_params(const ggp_mcmc_args& a, const double*
     diag_add = 1.0 / (a.lamsim[j] * lamwos) + 1.0 / lamws;
 }
 
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, int t)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,7 +161,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
 }
 
 // mode 0: sigwl <- per-PC terms of the current state.  mode 1: sigwl_cand <- terms under candidate lamWOs.
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride,
                 double* __restrict__ sig_cand, int mode)
 {
@@ -288,7 +288,9 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     }
     cudaStream_t st = (cudaStream_t)stream;
     GGP_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
     GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
 
     const size_t P = (size_t)a.d * a.pu + 2 * a.pu + 1;
     unsigned char* p = reinterpret_cast<unsigned char*>(a.workspace);

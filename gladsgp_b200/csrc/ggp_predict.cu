@@ -51,6 +51,8 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int nP = Mp >> 5;
+    __shared__ int soff[1024];
+    fill_slab_offsets(soff, Mp);
     const int nblk = (n + PB - 1) / PB;
     const long long ntask = (long long)B * nblk;
     double* __restrict__ Vw = Vws + (size_t)blockIdx.x * Mp * PB;   // [nP*4][PB][8]
@@ -93,7 +95,7 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     int rb[2] = {8 * (warp + NWARP * (2 * h)), 8 * (warp + NWARP * (2 * h + 1))};
-                    panel_gemm<2>(*reinterpret_cast<double (*)[2][4][2]>(&acc[2 * h]), Vw, Lp, Mp, j, row0, rb, g, q, PB);
+                    panel_gemm<2>(*reinterpret_cast<double (*)[2][4][2]>(&acc[2 * h]), Vw, Lp, soff, j, row0, rb, g, q, PB);
                 }
             }
             // ---- 2. cross-covariance entries, P = S21^T - S
@@ -332,6 +334,7 @@ int ggp_predict_f64(const double* X, int m, int d, const double* factor, const d
 {
     GGP_ARG(X && factor && u && beta && lamz && s11_diag && Xp && mean_out && var_out && workspace, "null pointer");
     GGP_ARG(m > 0 && d > 0 && n > 0 && B > 0, "m, d, n, B must be positive");
+    GGP_ARG(m <= 8192, "m must be <= 8192");
     const int Mp = round_up32(m);
     const size_t smem = pred_smem_bytes(Mp, d);
     if (smem > 227 * 1024) {

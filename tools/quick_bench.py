@@ -8,6 +8,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gladsgp_b200 import _lib  # noqa: E402
+if os.environ.get('GGP_LIB'):
+    _lib.LIB_PATH = os.environ['GGP_LIB']
 from gladsgp_b200 import ops, synthetic  # noqa: E402
 
 
@@ -41,7 +44,8 @@ def main():
     t = synthetic.design(m, q)
     X = np.concatenate([0.5 * np.ones((m, 1)), t.astype(np.float64)], axis=1)
     rng = np.random.default_rng(0)
-    for B in (1, 10, 148, 296, 444, 888):
+    Bs = [int(x) for x in os.environ.get('GGP_BS', '1,10,148,296,444,888').split(',')]
+    for B in Bs:
         beta = np.exp(rng.uniform(np.log(0.05), np.log(3.0), size=(B, d)))
         lamz = rng.uniform(0.5, 2.0, B); dadd = rng.uniform(1e-3, 1e-2, B)
         W = rng.standard_normal((B, m))
@@ -51,6 +55,8 @@ def main():
         best, med = ev_time(lambda: ops.loglik_batched(Xd, Wd, bd, ld, dd, factor_ws=ws), iters=5)
         fl = B * (m ** 3 / 3 + m * m)
         res['loglik_m512_B%d' % B] = dict(ms=best, ms_median=med, evals_per_s=B / best * 1e3, tflops=fl / best / 1e9)
+        if os.environ.get('GGP_NOCOV'):
+            continue
         best, med = ev_time(lambda: ops.cov_build(Xd, bd, ld, dd), iters=5)
         res['cov_m512_B%d' % B] = dict(ms=best, gbs=B * m * m * 8 / best / 1e6)
     print(json.dumps(res, indent=1))
