@@ -303,7 +303,7 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--chains', type=int, default=74, help='independent chains per GPU (74*10 CTAs = 5 waves of 148 SMs)')
+    ap.add_argument('--chains', type=int, default=44, help='independent chains per GPU (44*10 CTAs fill 148 SMs x 3 resident CTAs)')
     ap.add_argument('--nx', type=int, default=4000, help='field nodes (cfg3: 4k)')
     ap.add_argument('--nt', type=int, default=365, help='field time steps (cfg3: 365)')
     ap.add_argument('--ref-nx', type=int, default=400)

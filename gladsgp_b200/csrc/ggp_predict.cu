@@ -15,22 +15,25 @@
 
 namespace ggp {
 
-constexpr int PB = PASS_ROWS;     // designs per task (one TRSM row per thread)
+constexpr int PB = 256;           // designs per task: 8 warps x 4 units x 8 rows
 
 struct PredSmem {
-    double* LT;     // [32][LT_LD]
-    double* rdiag;  // [32]
+    double* Minv;   // [32][MI_LD] inverted diagonal block of the current panel (from the packed factor)
     double* uj;     // [32]
-    double* Ps;     // [PB][PS_LD]
-    double* S;      // [Mp][d] scaled training coordinates
-    double* Sp;     // [PB][d] scaled design coordinates
+    double* etab;   // [32]
+    double* sb;     // [d]
+    double* SC;     // [d][32] scaled training coordinates of the current panel
 };
 
-__host__ __device__ inline size_t pred_smem_bytes(int Mp, int d) {
-    return (size_t)(32 * LT_LD + 32 + 32 + PB * PS_LD + (size_t)Mp * d + (size_t)PB * d) * sizeof(double);
+__host__ __device__ inline size_t pred_smem_bytes(int d) {
+    return (size_t)(32 * MI_LD + 32 + 32 + 34 * ((d + 1) & ~1)) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(NT, 1)
+// One CTA pushes blocks of PB test designs through the cached factor of block b.  Rows = designs: each
+// warp owns four 8-row units; per panel  S = V[:,0:32j] L[panel,0:32j]^T (DMMA),  P = cross-cov - S,
+// X = P Minv^T (DMMA), V[:,panel] = X.  A lane reads back exactly the V entries it wrote (accumulator and
+// A-fragment layouts coincide under the k permutation), so V needs no block-level synchronisation.
+__global__ void __launch_bounds__(NT, 2)
 predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double* __restrict__ factor,
                long long l_stride, const double* __restrict__ U, const double* __restrict__ beta,
                const double* __restrict__ lamz, const double* __restrict__ s11,
@@ -41,144 +44,90 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
     PredSmem sm;
     {
         double* p = reinterpret_cast<double*>(smem_raw);
-        sm.LT = p;    p += 32 * LT_LD;
-        sm.rdiag = p; p += 32;
+        sm.Minv = p;  p += 32 * MI_LD;
         sm.uj = p;    p += 32;
-        sm.Ps = p;    p += PB * PS_LD;
-        sm.S = p;     p += (size_t)Mp * d;
-        sm.Sp = p;
+        sm.etab = p;  p += 32;
+        sm.SC = p;    p += 32 * ((d + 1) & ~1);
+        sm.sb = p;
     }
+    __shared__ int soff[1024];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int nP = Mp >> 5;
-    __shared__ int soff[1024];
     fill_slab_offsets(soff, Mp);
+    fill_exp_table(sm.etab);
     const int nblk = (n + PB - 1) / PB;
     const long long ntask = (long long)B * nblk;
     double* __restrict__ Vw = Vws + (size_t)blockIdx.x * Mp * PB;   // [nP*4][PB][8]
-    int cur_b = -1;
 
     for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
         const int b = (int)(task / nblk);
         const int t0 = (int)(task - (long long)b * nblk) * PB;
         const int nt = min(PB, n - t0);
-        const double* be = beta + (size_t)b * d;
         const double inv_lamz = 1.0 / lamz[b];
         const double* __restrict__ Lp = factor + (size_t)b * l_stride;
         const double* __restrict__ ub = U + (size_t)b * Mp;
         __syncthreads();
-        if (b != cur_b) {
-            for (int idx = tid; idx < Mp * d; idx += NT) {
-                int r = idx / d, k = idx - r * d;
-                sm.S[idx] = (r < m) ? X[(size_t)r * d + k] * sqrt(be[k]) : 0.0;
-            }
-            cur_b = b;
-        }
-        for (int idx = tid; idx < PB * d; idx += NT) {
-            int r = idx / d, k = idx - r * d;
-            sm.Sp[idx] = (r < nt) ? Xp[(size_t)(t0 + r) * d + k] * sqrt(be[k]) : 0.0;
-        }
-        double mean = 0.0, vsum = 0.0;
-        __syncthreads();
+        if (tid < d) sm.sb[tid] = sqrt(beta[(size_t)b * d + tid]);
+        double mean[4], vsum[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { mean[i] = 0.0; vsum[i] = 0.0; }
 
         for (int j = 0; j < nP; ++j) {
             const int row0 = j << 5;
-            const int Rj = Mp - row0;
-            const double* __restrict__ Lpj = Lp + panel_off(j, Mp);
-            // ---- 1. S = V[:, 0:32j] * L[panel rows, 0:32j]^T on the FP64 tensor cores
-            double acc[4][4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
-            if (j > 0) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    int rb[2] = {8 * (warp + NWARP * (2 * h)), 8 * (warp + NWARP * (2 * h + 1))};
-                    panel_gemm<2>(*reinterpret_cast<double (*)[2][4][2]>(&acc[2 * h]), Vw, Lp, soff, j, row0, rb, g, q, PB);
-                }
-            }
-            // ---- 2. cross-covariance entries, P = S21^T - S
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = 8 * (warp + NWARP * i) + g;          // local design index
-                const double* Sr = sm.Sp + (size_t)r * d;
-#pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int c = row0 + 8 * cb + 2 * q + e;   // training point
-                        double v = 0.0;
-                        if (r < nt && c < m) {
-                            const double* Sc = sm.S + (size_t)c * d;
-                            double dist = 0.0;
-                            for (int k = 0; k < d; ++k) {
-                                double t = Sr[k] - Sc[k];
-                                dist = fma(t, t, dist);
-                            }
-                            v = exp(-dist) * inv_lamz;
-                        }
-                        sm.Ps[r * PS_LD + (c - row0)] = v - acc[i][cb][e];
-                    }
-                }
-            }
-            // diagonal block of the factor -> LT, rdiag ; u block
-            for (int idx = tid; idx < 1024; idx += NT) {
-                const int i = idx >> 5, k = idx & 31;              // L[row0+i][row0+k]
-                const double v = Lpj[(long long)(k >> 3) * Rj * 8 + (long long)i * 8 + (k & 7)];
-                sm.LT[k * LT_LD + i] = v;
-                if (i == k) sm.rdiag[k] = 1.0 / v;
-            }
+            __syncthreads();                       // previous panel done with Minv / uj / SC (and sb visible)
+            fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
+            for (int idx = tid; idx < 1024; idx += NT)
+                sm.Minv[(idx >> 5) * MI_LD + (idx & 31)] = Lp[minv_off(Mp) + 1024LL * j + idx];
             if (tid < 32) sm.uj[tid] = ub[row0 + tid];
             __syncthreads();
-
-            // ---- 3. one design per thread: x <- x * Ljj^-T ; accumulate mean and sum of squares
-            double x[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) x[c] = sm.Ps[tid * PS_LD + c];
+            for (int h = 0; h < 2; ++h) {
+                double acc[2][4][2];
+                int rb[2];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const double xc = x[c] * sm.rdiag[c];
-                x[c] = xc;
-                const double* lt = sm.LT + c * LT_LD;
-                if (((c + 1) & 1) && c + 1 < 32) x[c + 1] = fma(-xc, lt[c + 1], x[c + 1]);
+                for (int i = 0; i < 2; ++i) {
+                    rb[i] = 8 * (warp + NWARP * (2 * h + i));
 #pragma unroll
-                for (int cp = (c + 2) & ~1; cp < 32; cp += 2) {
-                    const double2 l2 = *reinterpret_cast<const double2*>(lt + cp);
-                    x[cp] = fma(-xc, l2.x, x[cp]);
-                    x[cp + 1] = fma(-xc, l2.y, x[cp + 1]);
+                    for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
+                }
+                if (j > 0) panel_gemm<2>(acc, Vw, Lp, soff, j, row0, rb, g, q, PB);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = rb[i] + g;                       // local design index
+                    unit_cov(acc[i], Xp + (size_t)t0 * d, r, r < nt, sm.SC, sm.sb, d, m, row0, q, inv_lamz, 0.0, false,
+                             sm.etab);
+                    double xt[4][2];
+                    unit_trsm(acc[i], xt, sm.Minv, g, q);
+                    double s0 = 0.0, q0 = 0.0;
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        const double2 u2 = *reinterpret_cast<const double2*>(sm.uj + 8 * cb + 2 * q);
+                        s0 = fma(xt[cb][0], u2.x, s0);
+                        s0 = fma(xt[cb][1], u2.y, s0);
+                        q0 = fma(xt[cb][0], xt[cb][0], q0);
+                        q0 = fma(xt[cb][1], xt[cb][1], q0);
+                        *reinterpret_cast<double2*>(Vw + ((size_t)(4 * j + cb) * PB + r) * 8 + 2 * q) =
+                            make_double2(xt[cb][0], xt[cb][1]);
+                        if (V_out && r < nt)
+                            *reinterpret_cast<double2*>(V_out + ((size_t)b * n + t0 + r) * Mp + row0 + 8 * cb + 2 * q) =
+                                make_double2(xt[cb][0], xt[cb][1]);
+                    }
+                    mean[2 * h + i] += s0;
+                    vsum[2 * h + i] += q0;
                 }
             }
-            {
-                double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    const double2 u2 = *reinterpret_cast<const double2*>(sm.uj + c);
-                    s0 = fma(x[c], u2.x, s0);
-                    s1 = fma(x[c + 1], u2.y, s1);
-                    q0 = fma(x[c], x[c], q0);
-                    q1 = fma(x[c + 1], x[c + 1], q1);
-                }
-                mean += s0 + s1;
-                vsum += q0 + q1;
-            }
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                double* dst = Vw + ((size_t)(4 * j + ks) * PB + tid) * 8;
-#pragma unroll
-                for (int c = 0; c < 8; c += 2)
-                    *reinterpret_cast<double2*>(dst + c) = make_double2(x[8 * ks + c], x[8 * ks + c + 1]);
-            }
-            if (V_out && tid < nt) {
-                double* vo = V_out + ((size_t)b * n + t0 + tid) * Mp + row0;
-#pragma unroll
-                for (int c = 0; c < 32; c += 2) *reinterpret_cast<double2*>(vo + c) = make_double2(x[c], x[c + 1]);
-            }
-            __syncthreads();
         }
-        if (tid < nt) {
-            mean_out[(size_t)b * n + t0 + tid] = mean;
-            var_out[(size_t)b * n + t0 + tid] = s11[b] - vsum;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double s = mean[i], v = vsum[i];
+            s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const int r = 8 * (warp + NWARP * i) + g;
+            if (q == 0 && r < nt) {
+                mean_out[(size_t)b * n + t0 + r] = s;
+                var_out[(size_t)b * n + t0 + r] = s11[b] - v;
+            }
         }
     }
 }
@@ -317,7 +266,7 @@ static int predict_grid(int B, int n)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long ntask = (long long)B * ((n + PB - 1) / PB);
-    return (int)(ntask < sms ? ntask : sms);
+    return (int)(ntask < 2LL * sms ? ntask : 2LL * sms);       // two CTAs per SM
 }
 
 long long ggp_predict_workspace_bytes(int m, int n, int B)
@@ -336,8 +285,8 @@ int ggp_predict_f64(const double* X, int m, int d, const double* factor, const d
     GGP_ARG(m > 0 && d > 0 && n > 0 && B > 0, "m, d, n, B must be positive");
     GGP_ARG(m <= 8192, "m must be <= 8192");
     const int Mp = round_up32(m);
-    const size_t smem = pred_smem_bytes(Mp, d);
-    if (smem > 227 * 1024) {
+    const size_t smem = pred_smem_bytes(d);
+    if (smem > 100 * 1024) {
         set_error("ggp_predict_f64: m=%d d=%d needs %zu B of shared memory (> 227 KB)", m, d, smem);
         return GGP_ERR_UNSUPPORTED;
     }
