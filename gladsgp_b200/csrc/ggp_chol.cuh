@@ -148,39 +148,55 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
                                                   const double* __restrict__ Lb, const int* __restrict__ soff, int j,
                                                   int row0, const int (&rb)[2], int g, int q, int a_ld)
 {
-    constexpr int PDA = 6, PDB = 2;
-    const int nsl = 4 * j;
+    constexpr int PD = 2;                    // prefetch distance in k-blocks (4 sub-slabs each)
     const int lane = 4 * g + q;
+    // sub-slab pointers: packed factor -> soff table; V workspace (a_ld != 0) -> s * a_ld * 8
     auto a_slab = [&](int s) -> const double* { return a_ld ? Ap + (size_t)s * a_ld * 8 : Ap + soff[s]; };
+    // prefetch roles, one 128-byte line per lane and sub-slab group:
+    //   A: unit (lane>>4)%NU, sub-slab (lane>>2)&3, line lane&3      (NU*16 lines per k-block)
+    //   B: sub-slab lane>>3 (two passes: +0 / +... ) see below
+    const int pa_unit = ((lane >> 4) < NU) ? (lane >> 4) : 0;
+    const int pa_ks = (lane >> 2) & 3;
+    const int pa_off = rb[pa_unit] * 8 + (lane & 3) * 16;
+    const int pb_ks = lane >> 3;                                      // 8 lanes per sub-slab, 2 lines each
+    const int pb_off = (row0 + 4 * (lane & 7)) * 8;
     double2 an[NU];
     {
         const double* sl = a_slab(0);
 #pragma unroll
         for (int i = 0; i < NU; ++i) an[i] = ldcg2(sl + (rb[i] + g) * 8 + 2 * q);
     }
-    // prefetch roles
-    const int pf_unit = (lane >> 2) < NU ? (lane >> 2) : 0;
-    const int pf_arow = rb[pf_unit] * 8 + (lane & 3) * 16;          // A: 4 lines of 128 B per unit
-    const int pf_brow = (row0 + 2 * (lane & 15)) * 8;               // B: 16 lines of 128 B per sub-slab
-    for (int s = 0; s < nsl; ++s) {
-        const double* sl = Lb + soff[s];
-        double2 a[NU];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) a[i] = an[i];
-        if (s + 1 < nsl) {
-            const double* sn = a_slab(s + 1);
-#pragma unroll
-            for (int i = 0; i < NU; ++i) an[i] = ldcg2(sn + (rb[i] + g) * 8 + 2 * q);
+    for (int kb = 0; kb < j; ++kb) {
+        if (kb + PD < j) {
+            const int sp = 4 * (kb + PD);
+            prefetch_l2(a_slab(sp + pa_ks) + pa_off);
+            const double* pb = Lb + soff[sp + pb_ks] + pb_off;
+            prefetch_l1(pb);
+            prefetch_l1(pb + 16);
         }
-        if (lane < 4 * NU) { if (s + PDA < nsl) prefetch_l2(a_slab(s + PDA) + pf_arow); }
-        else if (lane >= 16) { if (s + PDB < nsl) prefetch_l1(Lb + soff[s + PDB] + pf_brow); }
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-            const double2 b = *reinterpret_cast<const double2*>(sl + (row0 + 8 * cb + g) * 8 + 2 * q);
+        for (int ks = 0; ks < 4; ++ks) {
+            const int s = 4 * kb + ks;
+            const double* sl = Lb + soff[s];
+            double2 a[NU];
 #pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b.x);
-                dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b.y);
+            for (int i = 0; i < NU; ++i) a[i] = an[i];
+            if (ks < 3 || kb + 1 < j) {
+                const double* sn = a_slab(s + 1);
+#pragma unroll
+                for (int i = 0; i < NU; ++i) an[i] = ldcg2(sn + (rb[i] + g) * 8 + 2 * q);
+            }
+            double2 b[4];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb)
+                b[cb] = *reinterpret_cast<const double2*>(sl + (row0 + 8 * cb + g) * 8 + 2 * q);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) {
+                    dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b[cb].x);
+                    dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b[cb].y);
+                }
             }
         }
     }
@@ -215,8 +231,10 @@ static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double*
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) { dist[cb][0] = 0.0; dist[cb][1] = 0.0; }
     const double* xr = Xr + (size_t)(row_ok ? r : 0) * d;
+    double xnext = __ldg(xr);
     for (int k = 0; k < d; ++k) {
-        const double sr = __ldg(xr + k) * sb[k];
+        const double sr = xnext * sb[k];
+        if (k + 1 < d) xnext = __ldg(xr + k + 1);
         const double* sc = SC + k * 32 + 2 * q;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {

@@ -29,10 +29,13 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 constexpr int NB = 32;          // panel width of the blocked factorisation
-constexpr int NT = 256;         // threads per CTA of the fused kernels (two CTAs share an SM)
+#ifndef GGP_NT
+#define GGP_NT 128
+#endif
+constexpr int NT = GGP_NT;      // threads per CTA of the fused kernels
 constexpr int NWARP = NT / 32;
 #ifndef GGP_CTAS_PER_SM
-#define GGP_CTAS_PER_SM 3     // register budget of the fused kernels: 65536 / (256 * CTAs)
+#define GGP_CTAS_PER_SM 4     // 4 warps x 4 CTAs per SM, 128 registers per thread (tools/quick_bench.py sweep)
 #endif
 constexpr int PASS_UNITS = 4 * NWARP;      // 8-row units per pass (4 per warp: 64 accumulator registers)
 constexpr int PASS_ROWS = 8 * PASS_UNITS;  // rows handled per pass

@@ -15,6 +15,8 @@
 
 namespace ggp {
 
+constexpr int PNT = 256;          // threads of the prediction kernel
+constexpr int PNW = PNT / 32;
 constexpr int PB = 256;           // designs per task: 8 warps x 4 units x 8 rows
 
 struct PredSmem {
@@ -33,7 +35,7 @@ __host__ __device__ inline size_t pred_smem_bytes(int d) {
 // warp owns four 8-row units; per panel  S = V[:,0:32j] L[panel,0:32j]^T (DMMA),  P = cross-cov - S,
 // X = P Minv^T (DMMA), V[:,panel] = X.  A lane reads back exactly the V entries it wrote (accumulator and
 // A-fragment layouts coincide under the k permutation), so V needs no block-level synchronisation.
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(PNT, 2)
 predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double* __restrict__ factor,
                long long l_stride, const double* __restrict__ U, const double* __restrict__ beta,
                const double* __restrict__ lamz, const double* __restrict__ s11,
@@ -77,7 +79,7 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
             const int row0 = j << 5;
             __syncthreads();                       // previous panel done with Minv / uj / SC (and sb visible)
             fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
-            for (int idx = tid; idx < 1024; idx += NT)
+            for (int idx = tid; idx < 1024; idx += PNT)
                 sm.Minv[(idx >> 5) * MI_LD + (idx & 31)] = Lp[minv_off(Mp) + 1024LL * j + idx];
             if (tid < 32) sm.uj[tid] = ub[row0 + tid];
             __syncthreads();
@@ -87,7 +89,7 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
                 int rb[2];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    rb[i] = 8 * (warp + NWARP * (2 * h + i));
+                    rb[i] = 8 * (warp + PNW * (2 * h + i));
 #pragma unroll
                     for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
                 }
@@ -123,7 +125,7 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
             double s = mean[i], v = vsum[i];
             s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-            const int r = 8 * (warp + NWARP * i) + g;
+            const int r = 8 * (warp + PNW * i) + g;
             if (q == 0 && r < nt) {
                 mean_out[(size_t)b * n + t0 + r] = s;
                 var_out[(size_t)b * n + t0 + r] = s11[b] - v;
@@ -296,7 +298,7 @@ int ggp_predict_f64(const double* X, int m, int d, const double* factor, const d
         return GGP_ERR_WORKSPACE;
     }
     GGP_CUDA(cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    predict_kernel<<<predict_grid(B, n), NT, smem, (cudaStream_t)stream>>>(
+    predict_kernel<<<predict_grid(B, n), PNT, smem, (cudaStream_t)stream>>>(
         X, m, Mp, d, factor, packed_doubles(Mp), u, beta, lamz, s11_diag, Xp, n, B, mean_out, var_out, V_out,
         reinterpret_cast<double*>(workspace));
     GGP_CUDA(cudaGetLastError());
