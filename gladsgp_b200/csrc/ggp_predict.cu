@@ -170,90 +170,92 @@ pred_cov_kernel(const double* __restrict__ Xp, int n, int d, const double* __res
 
 // ---------------------------------------------------------------------------------------------
 // PC-basis reconstruction  y[r][c] = (sum_p w[r][p] K[p][c]) * sd[c] + mean[c]   (get_y), float32.
-// HBM-write bound: 4*R*n_y bytes.  One CTA = 1024 columns x RT rows; the K tile and the w rows sit
-// in shared memory, each thread owns 4 columns and 4 rows at a time, stores are streaming.
+// HBM-write bound: 4*R*n_y bytes.  Each thread owns 4 columns and keeps their K entries for all PCs in
+// registers (PUMAX x 4), the w rows of the CTA's row range sit in shared memory and are read as
+// broadcast LDS.128 (16 FMAs per load); stores are 16-byte streaming stores (512 B contiguous per warp).
 // ---------------------------------------------------------------------------------------------
 constexpr int RC_COLS = 1024;
-constexpr int RC_RT = 32;
+constexpr int RC_RT = 128;       // rows of w staged per shared-memory tile
 
-template <bool VEC>
+template <int PUMAX, bool VEC>
 __global__ void __launch_bounds__(256)
 reconstruct_kernel(const float* __restrict__ w, const float* __restrict__ K, const float* __restrict__ sd,
                    int sd_len, const float* __restrict__ mu, int mu_len, int R, int pu, long long n_y,
-                   float* __restrict__ y)
+                   int rows_per_cta, float* __restrict__ y)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* Ks = reinterpret_cast<float*>(smem_raw);           // [pu][RC_COLS]
-    float* ws = Ks + (size_t)pu * RC_COLS;                    // [RC_RT][pu4]
-    const int pu4 = (pu + 3) & ~3;
+    __shared__ __align__(16) float ws[RC_RT * PUMAX];
     const long long c0 = (long long)blockIdx.x * RC_COLS;
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < pu * RC_COLS; idx += 256) {
-        const int p = idx / RC_COLS, c = idx - p * RC_COLS;
-        Ks[idx] = (c0 + c < n_y) ? K[(size_t)p * n_y + c0 + c] : 0.f;
-    }
     long long col[4];
-    float sdv[4], muv[4];
+    float sdv[4], muv[4], kreg[PUMAX][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         col[i] = VEC ? c0 + 4 * tid + i : c0 + tid + 256 * i;
         const bool in = col[i] < n_y;
         sdv[i] = in ? (sd_len == 1 ? sd[0] : sd[col[i]]) : 0.f;
         muv[i] = in ? (mu_len == 1 ? mu[0] : mu[col[i]]) : 0.f;
+#pragma unroll
+        for (int p = 0; p < PUMAX; ++p) kreg[p][i] = (in && p < pu) ? __ldg(K + (size_t)p * n_y + col[i]) : 0.f;
     }
-    for (int r0 = blockIdx.y * RC_RT; r0 < R; r0 += gridDim.y * RC_RT) {
+    const int r_begin = blockIdx.y * rows_per_cta;
+    const int r_end = min(R, r_begin + rows_per_cta);
+    for (int r0 = r_begin; r0 < r_end; r0 += RC_RT) {
+        const int nr = min(RC_RT, r_end - r0);
         __syncthreads();
-        for (int idx = tid; idx < RC_RT * pu4; idx += 256) {
-            const int rr = idx / pu4, p = idx - rr * pu4;
-            ws[idx] = (r0 + rr < R && p < pu) ? w[(size_t)(r0 + rr) * pu + p] : 0.f;
+        for (int idx = tid; idx < nr * PUMAX; idx += 256) {
+            const int rr = idx / PUMAX, p = idx - rr * PUMAX;
+            ws[idx] = (p < pu) ? w[(size_t)(r0 + rr) * pu + p] : 0.f;
         }
         __syncthreads();
-        for (int rg = 0; rg < RC_RT; rg += 4) {
-            if (r0 + rg >= R) break;
-            float acc[4][4];
+#pragma unroll 2
+        for (int rr = 0; rr < nr; ++rr) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int p4 = 0; p4 < PUMAX; p4 += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(ws + rr * PUMAX + p4);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
-            for (int p = 0; p < pu; ++p) {
-                float kv[4];
-                if (VEC) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(Ks + (size_t)p * RC_COLS + 4 * tid);
-                    kv[0] = k4.x; kv[1] = k4.y; kv[2] = k4.z; kv[3] = k4.w;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) kv[c] = Ks[(size_t)p * RC_COLS + tid + 256 * c];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float wv = ws[(rg + i) * pu4 + p];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(wv, kv[c], acc[i][c]);
+                for (int c = 0; c < 4; ++c) {
+                    acc[c] = fmaf(w4.x, kreg[p4 + 0][c], acc[c]);
+                    acc[c] = fmaf(w4.y, kreg[p4 + 1][c], acc[c]);
+                    acc[c] = fmaf(w4.z, kreg[p4 + 2][c], acc[c]);
+                    acc[c] = fmaf(w4.w, kreg[p4 + 3][c], acc[c]);
                 }
             }
+            float* yr = y + (size_t)(r0 + rr) * n_y;
+            if (VEC && col[3] < n_y) {
+                __stcs(reinterpret_cast<float4*>(yr + col[0]),
+                       make_float4(acc[0] * sdv[0] + muv[0], acc[1] * sdv[1] + muv[1], acc[2] * sdv[2] + muv[2],
+                                   acc[3] * sdv[3] + muv[3]));
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + rg + i;
-                if (r >= R) break;
-                float* yr = y + (size_t)r * n_y;
-                if (VEC) {
-                    if (col[3] < n_y) {
-                        float4 o = make_float4(acc[i][0] * sdv[0] + muv[0], acc[i][1] * sdv[1] + muv[1],
-                                               acc[i][2] * sdv[2] + muv[2], acc[i][3] * sdv[3] + muv[3]);
-                        __stcs(reinterpret_cast<float4*>(yr + col[0]), o);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (col[c] < n_y) __stcs(yr + col[c], acc[i][c] * sdv[c] + muv[c]);
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (col[c] < n_y) __stcs(yr + col[c], acc[i][c] * sdv[c] + muv[c]);
-                }
+                for (int c = 0; c < 4; ++c)
+                    if (col[c] < n_y) __stcs(yr + col[c], acc[c] * sdv[c] + muv[c]);
             }
         }
     }
+}
+
+template <int PUMAX>
+static int launch_reconstruct(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
+                              int mean_len, int R, int pu, long long n_y, float* y_out, cudaStream_t st)
+{
+    const unsigned gx = (unsigned)((n_y + RC_COLS - 1) / RC_COLS);
+    // enough CTAs to fill the machine a few times over, but long row ranges per CTA (K is loaded once per CTA)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned gy = (unsigned)((8u * sms + gx - 1) / gx);
+    const unsigned gymax = (unsigned)((R + 31) / 32);
+    if (gy > gymax) gy = gymax;
+    if (gy < 1) gy = 1;
+    const int rows_per_cta = (R + gy - 1) / gy;
+    gy = (unsigned)((R + rows_per_cta - 1) / rows_per_cta);
+    const bool vec = (n_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(y_out) & 15) == 0);
+    if (vec)
+        reconstruct_kernel<PUMAX, true><<<dim3(gx, gy), 256, 0, st>>>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, rows_per_cta, y_out);
+    else
+        reconstruct_kernel<PUMAX, false><<<dim3(gx, gy), 256, 0, st>>>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, rows_per_cta, y_out);
+    return 0;
 }
 
 }  // namespace ggp
@@ -322,21 +324,14 @@ int ggp_reconstruct_f32(const float* w, const float* K, const float* sd, int sd_
     GGP_ARG(w && K && sd && mean && y_out, "null pointer");
     GGP_ARG(R > 0 && pu > 0 && n_y > 0, "R, pu, n_y must be positive");
     GGP_ARG((sd_len == 1 || sd_len == n_y) && (mean_len == 1 || mean_len == n_y), "sd/mean length must be 1 or n_y");
-    const int pu4 = (pu + 3) & ~3;
-    const size_t smem = ((size_t)pu * RC_COLS + (size_t)RC_RT * pu4) * sizeof(float);
-    GGP_ARG(smem <= 200 * 1024, "pu too large for reconstruct");
-    const unsigned gx = (unsigned)((n_y + RC_COLS - 1) / RC_COLS);
-    unsigned gy = (unsigned)((R + RC_RT - 1) / RC_RT);
-    if (gy > 65535u) gy = 65535u;
-    const bool vec = (n_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(y_out) & 15) == 0);
+    GGP_ARG(pu <= 32, "pu must be <= 32");
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec) {
-        GGP_CUDA(cudaFuncSetAttribute(reconstruct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reconstruct_kernel<true><<<dim3(gx, gy), 256, smem, st>>>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out);
-    } else {
-        GGP_CUDA(cudaFuncSetAttribute(reconstruct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reconstruct_kernel<false><<<dim3(gx, gy), 256, smem, st>>>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out);
-    }
+    if (pu <= 4) launch_reconstruct<4>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
+    else if (pu <= 8) launch_reconstruct<8>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
+    else if (pu <= 12) launch_reconstruct<12>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
+    else if (pu <= 16) launch_reconstruct<16>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
+    else if (pu <= 24) launch_reconstruct<24>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
+    else launch_reconstruct<32>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }
