@@ -190,14 +190,15 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
                 b[cb] = *reinterpret_cast<const double2*>(sl + (row0 + 8 * cb + g) * 8 + 2 * q);
+            // all even-k DMMAs first, then the odd-k ones: dependent DMMAs on one accumulator are 4*NU apart
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-                for (int i = 0; i < NU; ++i) {
-                    dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b[cb].x);
-                    dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b[cb].y);
-                }
-            }
+                for (int i = 0; i < NU; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b[cb].x);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                for (int i = 0; i < NU; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b[cb].y);
         }
     }
 }
@@ -354,12 +355,16 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         int rb0[2];
         const int nu0 = make_pair(0, acc0, rb0);
         GGP_TICK(1);
-        if (warp < 4) {
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb)
+        for (int i = 0; i < 2; ++i) {
+            const int u = warp + NWARP * i;          // units 0..3 are the diagonal block
+            if (i < nu0 && u < 4) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    D[(8 * warp + g) * D_LD + 8 * cb + 2 * q + e] = acc0[0][cb][e];
+                for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        D[(8 * u + g) * D_LD + 8 * cb + 2 * q + e] = acc0[i][cb][e];
+            }
         }
         __syncthreads();                                                         // (A)
         GGP_TICK(2);
@@ -484,8 +489,8 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         GGP_TICK(6);
 
         // ---------------------------------------------------------------------- finish the held pair, then the rest
-        if (nu0 >= 1 && warp >= 4) finish_unit(acc0[0], rb0[0]);     // t = 0 of warps 0..3 is the diagonal block
-        if (nu0 >= 2) finish_unit(acc0[1], rb0[1]);
+        if (nu0 >= 1 && warp >= 4) finish_unit(acc0[0], rb0[0]);                 // units 0..3 are the diagonal block
+        if (nu0 >= 2 && warp + NWARP >= 4) finish_unit(acc0[1], rb0[1]);
         for (int t0 = 2; t0 < nmy; t0 += 2) {
             double acc[2][4][2];
             int rb[2];

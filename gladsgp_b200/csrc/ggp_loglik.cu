@@ -1,5 +1,6 @@
 // Covariance build, cross-covariance and batched fused log-likelihood entry points.
 // C-ABI declared in include/gladsgp_b200.h.
+#include <cstdlib>
 #include "ggp_chol.cuh"
 #include "../../include/gladsgp_b200.h"
 
@@ -245,8 +246,11 @@ int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long 
     cudaStream_t st = (cudaStream_t)stream;
     GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
+    // GGP_DEBUG_SHARED_WS=1 (developer experiment): every CTA scribbles over the same workspace, results are
+    // garbage, timing shows the kernel with an L2-resident factor
+    static const bool shared_ws = getenv("GGP_DEBUG_SHARED_WS") != nullptr;
     loglik_batched_kernel<<<B, NT, smem, st>>>(X, m, Mp, d, W, w_stride, beta, lamz, diag_add, factor_ws,
-                                               packed_doubles(Mp), u_out, loglik_out, info_out);
+                                               shared_ws ? 0 : packed_doubles(Mp), u_out, loglik_out, info_out);
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }
