@@ -146,3 +146,26 @@ def test_in_kernel_exponential_accuracy(cuda):
     rel = np.abs(got - ref) / ref
     assert rel.max() < 4.5e-16, rel.max()
     assert got[-1] == 1.0
+
+
+def test_loglik_large_m_many_inputs(cuda):
+    """cfg 5 shape class (m in the thousands, d = 17): single-CTA path, multi-pass panels."""
+    import scipy.linalg
+    from gladsgp_b200 import ops, synthetic
+    m, q = 1500, 16
+    t = synthetic.design(m, q)
+    X = np.concatenate([0.5 * np.ones((m, 1)), t.astype(np.float64)], axis=1)
+    rng = np.random.default_rng(0)
+    beta = np.exp(rng.uniform(np.log(0.05), np.log(1.0), size=(2, q + 1)))
+    lamz = np.array([0.9, 1.4]); dadd = np.array([2e-3, 5e-3])
+    W = rng.standard_normal((2, m))
+    out = ops.loglik_batched(X, W, beta, lamz, dadd)
+    ll = out['loglik'].cpu().numpy()
+    for b in range(2):
+        D = ((X[:, None, :] - X[None, :, :]) ** 2) @ beta[b]
+        C = np.exp(-D) / lamz[b]
+        np.fill_diagonal(C, 1 / lamz[b] + dadd[b])
+        L = scipy.linalg.cholesky(C, lower=True)
+        u = scipy.linalg.solve_triangular(L, W[b], lower=True)
+        ref = -np.sum(np.log(np.diag(L))) - 0.5 * u @ u
+        assert abs(ll[b] - ref) <= LL_RTOL * abs(ref)
