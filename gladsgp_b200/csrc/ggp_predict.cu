@@ -235,6 +235,110 @@ reconstruct_kernel(const float* __restrict__ w, const float* __restrict__ K, con
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused predictive-distribution statistics (the post-processing every caller does right
+// after get_y: assess_all_models.py:493-500, plot_test_error.py:81-87).  For design t and output c, over the
+// posterior samples s:   y_s = (w[s][t] . K[:,c]) * sd[c] + mu[c],   z_s = y_s + sd[c] * noise[s][t]
+//   ymean = mean_s y_s ,  ylo / yhi = q and 1-q quantiles of z_s (np.quantile, linear interpolation).
+// The per-sample fields never touch HBM: each thread streams the samples for 4 columns and keeps only the
+// KQ smallest and KQ largest values (the quantiles the reference uses, 2.5 % / 97.5 % of 64-128 samples,
+// need 3-5 of them).
+// ---------------------------------------------------------------------------------------------
+template <int PUMAX, int KQ>
+__global__ void __launch_bounds__(256)
+reconstruct_stats_kernel(const float* __restrict__ w, const float* __restrict__ K, const float* __restrict__ sd,
+                         int sd_len, const float* __restrict__ mu, int mu_len, const float* __restrict__ noise,
+                         int nsamp, int npred, int pu, long long n_y, int i0, float frac,
+                         float* __restrict__ ymean, float* __restrict__ ylo, float* __restrict__ yhi)
+{
+    extern __shared__ __align__(16) float ws[];          // [nsamp][PUMAX] then noise [nsamp]
+    float* ns = ws + (size_t)nsamp * PUMAX;
+    const int t = blockIdx.y;
+    const long long c0 = (long long)blockIdx.x * RC_COLS;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nsamp * PUMAX; idx += 256) {
+        const int s_ = idx / PUMAX, p = idx - s_ * PUMAX;
+        ws[idx] = (p < pu) ? w[((size_t)s_ * npred + t) * pu + p] : 0.f;
+    }
+    for (int s_ = tid; s_ < nsamp; s_ += 256) ns[s_] = noise ? noise[(size_t)s_ * npred + t] : 0.f;
+    long long col[4];
+    float sdv[4], muv[4], kreg[PUMAX][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        col[i] = c0 + tid + 256 * i;                       // coalesced scalar access (n_y may be odd)
+        const bool in = col[i] < n_y;
+        sdv[i] = in ? (sd_len == 1 ? sd[0] : sd[col[i]]) : 0.f;
+        muv[i] = in ? (mu_len == 1 ? mu[0] : mu[col[i]]) : 0.f;
+#pragma unroll
+        for (int p = 0; p < PUMAX; ++p) kreg[p][i] = (in && p < pu) ? __ldg(K + (size_t)p * n_y + col[i]) : 0.f;
+    }
+    __syncthreads();
+    float lo[4][KQ], hi[4][KQ], sum[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        sum[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) { lo[c][k] = INFINITY; hi[c][k] = -INFINITY; }
+    }
+    for (int s_ = 0; s_ < nsamp; ++s_) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int p4 = 0; p4 < PUMAX; p4 += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(ws + s_ * PUMAX + p4);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc[c] = fmaf(w4.x, kreg[p4 + 0][c], acc[c]);
+                acc[c] = fmaf(w4.y, kreg[p4 + 1][c], acc[c]);
+                acc[c] = fmaf(w4.z, kreg[p4 + 2][c], acc[c]);
+                acc[c] = fmaf(w4.w, kreg[p4 + 3][c], acc[c]);
+            }
+        }
+        const float e = ns[s_];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float yv = acc[c] * sdv[c] + muv[c];
+            sum[c] += yv;
+            const float z = yv + sdv[c] * e;
+            float v = z;
+#pragma unroll
+            for (int k = 0; k < KQ; ++k) { const float a = lo[c][k]; lo[c][k] = fminf(a, v); v = fmaxf(a, v); }
+            v = z;
+#pragma unroll
+            for (int k = 0; k < KQ; ++k) { const float a = hi[c][k]; hi[c][k] = fmaxf(a, v); v = fminf(a, v); }
+        }
+    }
+    const float inv_n = 1.f / (float)nsamp;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (col[c] < n_y) {
+            float a = 0.f, b = 0.f, ha = 0.f, hb = 0.f;
+#pragma unroll
+            for (int k = 0; k < KQ - 1; ++k)
+                if (k == i0) { a = lo[c][k]; b = lo[c][k + 1]; ha = hi[c][k + 1]; hb = hi[c][k]; }
+            const size_t o = (size_t)t * n_y + col[c];
+            __stcs(ymean + o, sum[c] * inv_n);
+            __stcs(ylo + o, a + (b - a) * frac);
+            __stcs(yhi + o, ha + (hb - ha) * (1.f - frac));
+        }
+    }
+}
+
+template <int PUMAX>
+static int launch_stats(const float* w, const float* K, const float* sd, int sd_len, const float* mean, int mean_len,
+                        const float* noise, int nsamp, int npred, int pu, long long n_y, int i0, float frac,
+                        float* ymean, float* ylo, float* yhi, cudaStream_t st)
+{
+    const dim3 grid((unsigned)((n_y + RC_COLS - 1) / RC_COLS), (unsigned)npred);
+    const size_t smem = ((size_t)nsamp * PUMAX + nsamp) * sizeof(float);
+    if (i0 + 2 <= 4)
+        reconstruct_stats_kernel<PUMAX, 4><<<grid, 256, smem, st>>>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu,
+                                                                   n_y, i0, frac, ymean, ylo, yhi);
+    else
+        reconstruct_stats_kernel<PUMAX, 8><<<grid, 256, smem, st>>>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu,
+                                                                   n_y, i0, frac, ymean, ylo, yhi);
+    return 0;
+}
+
 template <int PUMAX>
 static int launch_reconstruct(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
                               int mean_len, int R, int pu, long long n_y, float* y_out, cudaStream_t st)
@@ -332,6 +436,31 @@ int ggp_reconstruct_f32(const float* w, const float* K, const float* sd, int sd_
     else if (pu <= 16) launch_reconstruct<16>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
     else if (pu <= 24) launch_reconstruct<24>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
     else launch_reconstruct<32>(w, K, sd, sd_len, mean, mean_len, R, pu, n_y, y_out, st);
+    GGP_CUDA(cudaGetLastError());
+    return GGP_OK;
+}
+
+int ggp_reconstruct_stats_f32(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
+                              int mean_len, const float* noise, int nsamp, int npred, int pu, long long n_y, double q,
+                              float* ymean_out, float* ylo_out, float* yhi_out, void* stream)
+{
+    GGP_ARG(w && K && sd && mean && ymean_out && ylo_out && yhi_out, "null pointer");
+    GGP_ARG(nsamp > 1 && npred > 0 && pu > 0 && n_y > 0, "nsamp, npred, pu, n_y must be positive");
+    GGP_ARG((sd_len == 1 || sd_len == n_y) && (mean_len == 1 || mean_len == n_y), "sd/mean length must be 1 or n_y");
+    GGP_ARG(q > 0.0 && q < 0.5, "q must be in (0, 0.5)");
+    GGP_ARG(npred <= 65535, "npred must be <= 65535 per call");
+    const double pos = q * (nsamp - 1);
+    const int i0 = (int)floor(pos);
+    const float frac = (float)(pos - i0);
+    if (pu > 16 || i0 + 2 > 8 || i0 + 2 > nsamp || (size_t)nsamp * 17 * sizeof(float) > 200 * 1024) {
+        set_error("ggp_reconstruct_stats_f32: unsupported (pu=%d > 16 or quantile needs %d > 8 order statistics)", pu, i0 + 2);
+        return GGP_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pu <= 4) launch_stats<4>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st);
+    else if (pu <= 8) launch_stats<8>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st);
+    else if (pu <= 12) launch_stats<12>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st);
+    else launch_stats<16>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st);
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }

@@ -262,6 +262,28 @@ def reconstruct(w, K, sd, mean, out=None):
     return out
 
 
+def reconstruct_stats(w, K, sd, mean, q=0.025, noise=None):
+    """Fused get_y + mean / (q, 1-q) quantiles over samples.
+    w (nsamp,npred,pu) f32, noise (nsamp,npred) f32 or None -> (ymean, ylo, yhi), each (npred, n_y) f32 on the device."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = 'cuda'
+
+    def f32(t):
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.ascontiguousarray(np.asarray(t, dtype=np.float32)))
+        return t.to(device=dev, dtype=torch.float32).contiguous()
+    w = f32(w); K = f32(K); sd = f32(sd).reshape(-1); mean = f32(mean).reshape(-1)
+    nsamp, npred, pu = w.shape
+    n_y = K.shape[1]
+    nz = None if noise is None else f32(noise).reshape(nsamp, npred)
+    outs = [torch.empty((npred, n_y), dtype=torch.float32, device=dev) for _ in range(3)]
+    check(lib.ggp_reconstruct_stats_f32(ptr(w), ptr(K), ptr(sd), sd.numel(), ptr(mean), mean.numel(), ptr(nz), nsamp,
+                                        npred, pu, n_y, float(q), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), stream_ptr()),
+          'ggp_reconstruct_stats_f32')
+    return tuple(outs)
+
+
 def rsvd_sketch(X, omegaT, ws=None):
     """Y = X @ omega  (src/svd.py:52), omegaT = omega.T (r,n) f32 device tensor."""
     torch = _lib.require_cuda()

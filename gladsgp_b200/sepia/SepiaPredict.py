@@ -167,6 +167,21 @@ class SepiaEmulatorPrediction(SepiaPrediction):
         return y if device else y.cpu().numpy()
 
 
+    def get_y_stats(self, quantile=0.025, noise=None, device=False):
+        """Extension: mean over samples of get_y() and the (quantile, 1-quantile) quantiles of
+        get_y() + sd_y * noise[s, t], fused on the GPU -- the per-sample fields are never materialised.  This is
+        the post-processing of assess_all_models.py:493-500 / plot_test_error.py:81-87 (`noise[s, t]` there is
+        np.random.normal(scale=1/sqrt(lamWOs[s]))).  Returns dict(mean, lq, uq), each (npred, n_y) float32."""
+        sd = self.model.data.sim_data
+        if self.model.data.scalar_out:
+            raise NotImplementedError('get_y_stats is for multivariate (K basis) models')
+        m_, lo, hi = ops.reconstruct_stats(np.asarray(self.w, dtype=np.float32), sd.K, sd.orig_y_sd, sd.orig_y_mean,
+                                           q=quantile, noise=noise)
+        if device:
+            return dict(mean=m_, lq=lo, uq=hi)
+        return dict(mean=m_.cpu().numpy(), lq=lo.cpu().numpy(), uq=hi.cpu().numpy())
+
+
 class SepiaXvalEmulatorPrediction:
     """Imported, never called, by the reference (assess_all_models.py:31-32)."""
 

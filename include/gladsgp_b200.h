@@ -144,6 +144,16 @@ int ggp_pred_cov_f64(const double* Xp, int n, int d, const double* beta, const d
 int ggp_reconstruct_f32(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
                         int mean_len, int R, int pu, long long n_y, float* y_out, void* stream);
 
+/* Fused predictive-distribution statistics (what every caller does right after get_y:
+ * assess_all_models.py:493-500, plot_test_error.py:81-87), float32.  Over the posterior samples s, for design t
+ * and output c:  y_s = (w[s][t] . K[:,c]) * sd[c] + mean[c],  z_s = y_s + sd[c] * noise[s][t]  (noise nullable):
+ *   ymean = mean_s y_s;  ylo / yhi = q and 1-q quantiles of z_s (np.quantile, linear interpolation).
+ * w[nsamp][npred][pu], noise[nsamp][npred], outputs [npred][n_y].  Needs floor(q (nsamp-1)) + 2 <= 8 and pu <= 16
+ * (GGP_ERR_UNSUPPORTED otherwise). */
+int ggp_reconstruct_stats_f32(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
+                              int mean_len, const float* noise, int nsamp, int npred, int pu, long long n_y, double q,
+                              float* ymean_out, float* ylo_out, float* yhi_out, void* stream);
+
 /* ---- (4) randomized SVD passes -----------------------------------------------------------------
  * src/svd.py:52  Y = X @ omega           -> ggp_rsvd_sketch_f32 (OmegaT = omega^T, [r][n])
  * src/svd.py:56  Y = X @ X.T @ Y         -> ggp_rsvd_xty_f32 then ggp_rsvd_sketch_f32 (X (X^T Y))

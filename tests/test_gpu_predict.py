@@ -99,3 +99,23 @@ def test_rsvd_passes_match_numpy(cuda, m, n, r):
     Bt = ops.rsvd_xty(Xd, torch.as_tensor(Yq, device='cuda')).cpu().numpy()
     refB = Yq.astype(np.float64).T @ X.astype(np.float64)
     np.testing.assert_allclose(Bt, refB, rtol=0, atol=3e-5 * np.abs(refB).max())
+
+
+@pytest.mark.parametrize('nsamp,npred,n_y,q', [(64, 4, 3001, 0.025), (128, 1, 1000, 0.025), (16, 3, 2048, 0.05)])
+def test_fused_stats_match_numpy_postprocessing(cuda, nsamp, npred, n_y, q):
+    """assess_all_models.py:493-500: mean of get_y over samples, quantiles of get_y + sd_y * N(0, 1/lamWOs[s])."""
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(3)
+    pu = 10
+    w = rng.standard_normal((nsamp, npred, pu)).astype(np.float32)
+    K = rng.standard_normal((pu, n_y)).astype(np.float32)
+    sd = rng.uniform(0.1, 2.0, n_y).astype(np.float32); mu = rng.standard_normal(n_y).astype(np.float32)
+    noise = (rng.standard_normal((nsamp, npred)) / np.sqrt(rng.uniform(20, 200, (nsamp, 1)))).astype(np.float32)
+    y = so.get_y(w, K, sd, mu)                                   # (nsamp, npred, n_y)
+    z = y + sd[None, None, :] * noise[:, :, None]
+    ref_mean = np.mean(y, axis=0)
+    ref_lo = np.quantile(z, q, axis=0); ref_hi = np.quantile(z, 1 - q, axis=0)
+    m_, lo, hi = [t.cpu().numpy() for t in ops.reconstruct_stats(w, K, sd, mu, q=q, noise=noise)]
+    np.testing.assert_allclose(m_, ref_mean, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(lo, ref_lo, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(hi, ref_hi, rtol=1e-4, atol=1e-4)

@@ -52,6 +52,12 @@ def main():
     tr = ev(lambda: ops.reconstruct(w, K, sd, mu, out=out), iters=5, warm=2)
     res['reconstruct_ms'] = tr; res['reconstruct_gbs'] = 4.0 * R * n_y / tr / 1e6
     res['reconstruct_rows_per_s'] = R / tr * 1e3
+    # fused statistics: 64 samples x 4 designs (assess_all_models.py batch), mean + 2.5/97.5 % quantiles
+    ns_, np_ = 64, 4
+    w3 = torch.randn(ns_, np_, pu, device='cuda'); nz = torch.randn(ns_, np_, device='cuda') * 0.1
+    tst = ev(lambda: ops.reconstruct_stats(w3, K, sd, mu, q=0.025, noise=nz), iters=5, warm=2)
+    res['stats_ms_64x4'] = tst
+    res['stats_equiv_materialised_gbs'] = 4.0 * ns_ * np_ * n_y / tst / 1e6
     del out, K
     # rSVD passes on a 512 x 1.46M float32 ensemble
     Xe = torch.randn(m, n_y, device='cuda')
