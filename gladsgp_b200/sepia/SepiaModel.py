@@ -291,11 +291,13 @@ class SepiaModel:
         saved = [b.val.copy() for b in blocks]
         saved_lp = self.params.lp.val
         bar = _progress(n_burn, 'Step size tuning', prog)
-        _, _, acc = self._run(nsteps, sched, do_propMH=False, record_accept=True)
+        draws, lps, acc = self._run(nsteps, sched, do_propMH=False, record_accept=True)
         if bar is not None:
             bar.update(n_burn)
             bar.close()
+        self._store_state(draws[-1, 0, :])          # SEPIA copies the tuning chain's final values back
         final_blocks = [b.val.copy() for b in blocks]
+        final_lp = float(lps[-1, 0])
         acc = acc[warm:, 0, :].reshape(n_burn, n_levels, P).sum(axis=0)      # accepts per (level, element)
         target = np.log(1.0 / (np.exp(1.0) - 1.0))
         new_step = tb['step'].copy()
@@ -313,8 +315,7 @@ class SepiaModel:
             b.mcmc.stepParam = new_step[o:o + n].reshape(b.val_shape, order='F').copy()
             b.val = v1 if update_vals else v0
             o += n
-        if not update_vals:
-            self.params.lp.val = saved_lp
+        self.params.lp.val = final_lp if update_vals else saved_lp
         print('Done with tune_step_size.')
         print('Selected step sizes:')
         for prm in self.params.mcmcList:

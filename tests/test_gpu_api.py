@@ -164,3 +164,27 @@ def test_randomized_svd_matches_reference_algorithm(cuda):
     np.random.seed(9); svd.randomized_svd(X, 5, k=0, q=1); a = np.random.random_sample()
     np.random.seed(9); np.random.normal(size=(X.shape[1], 5)); b = np.random.random_sample()
     assert a == b
+
+
+def test_tune_step_sizes_matches_oracle(cuda):
+    """Same global stream -> same acceptance counts -> same selected step sizes as the oracle's tuner
+    (10 warm-up steps, ladder default*2^e, do_propMH=False, logit fit, target 1/e)."""
+    import contextlib, io
+    pr = make_problem(m=64, q=3, pu=2)
+    data, model = _build(pr, 3)
+    om = so.OracleModel(so.OracleNum(pr['t'], data.sim_data.y_std, pr['K']))
+    om.lamWOs.params = [p.copy() for p in model.params.lamWOs.prior.params]
+    np.random.seed(11)
+    om.tune_step_sizes(12, 4, rng=np.random)
+    after_oracle = np.random.random_sample()
+    np.random.seed(11)
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        model.tune_step_sizes(12, 4, prog=False)
+    after_gpu = np.random.random_sample()
+    assert after_gpu == after_oracle
+    txt = out.getvalue()
+    assert txt.startswith('Starting tune_step_sizes...\nDefault step sizes:\nbetaU\n')      # examples/04_*.ipynb:297-300
+    assert 'Done with tune_step_size.\nSelected step sizes:\n' in txt                        # :327-328
+    for name in ('betaU', 'lamUz', 'lamWs', 'lamWOs'):
+        np.testing.assert_allclose(getattr(model.params, name).mcmc.stepParam, getattr(om, name).step, rtol=1e-6)
+        np.testing.assert_allclose(getattr(model.params, name).val, getattr(om, name).val, rtol=1e-7)
