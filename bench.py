@@ -171,6 +171,77 @@ def fp64_peak_tflops(torch):
     return 2.0 * n ** 3 / best / 1e9
 
 
+def prediction_bench(torch, model, args, rank, world):
+    """Emulator predictions/s: one prediction = one (posterior sample, test design) pair -> pu PC means and
+    variances.  nsamp x pu covariance factors are cached once; test designs are sharded across ranks."""
+    import torch.distributed as dist
+    from gladsgp_b200 import ops, synthetic
+    from sepia.SepiaPredict import SepiaEmulatorPrediction
+    nsamp, npred = args.pred_samples, args.pred_designs
+    samples = synthetic.posterior_samples(nsamp, D, PU, seed=77)
+    tp = synthetic.test_design(npred * world, Q)[rank * npred:(rank + 1) * npred]
+    pr = SepiaEmulatorPrediction(t_pred=tp[:4], samples=samples, model=model, do_call=False)
+    ns, beta, lamz, dadd, s11, W = pr._blocks()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+    P0 = ops.Predictor(model.num.zt, W, beta, lamz, dadd, s11)            # warm-up (also keeps the factors)
+    xp = torch.as_tensor(np.concatenate([0.5 * np.ones((npred, 1)), tp.astype(np.float64)], axis=1), device='cuda')
+    P0.predict(xp[:512])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    P1 = ops.Predictor(model.num.zt, W, beta, lamz, dadd, s11)
+    e1.record()
+    mean, var = P1.predict(xp)
+    e2.record()
+    torch.cuda.synchronize()
+    fac_ms, prd_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    # end to end through the reference-facing class with host buffers (moments only, no joint covariance)
+    t0 = time.perf_counter()
+    pe = SepiaEmulatorPrediction(t_pred=tp[:1024], samples=samples, model=model, joint=False)
+    e2e_s = time.perf_counter() - t0
+    # reconstruction of a batch of fields (get_y), float32
+    w32 = pe.w[:, :4, :].astype(np.float32).reshape(-1, PU)
+    sd_ = model.data.sim_data
+    Kd = torch.as_tensor(np.asarray(sd_.K), device='cuda'); sdd = torch.as_tensor(np.asarray(sd_.orig_y_sd), device='cuda')
+    mud = torch.as_tensor(np.asarray(sd_.orig_y_mean), device='cuda'); wd = torch.as_tensor(w32, device='cuda')
+    out = ops.reconstruct(wd, Kd, sdd, mud)
+    torch.cuda.synchronize()
+    r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
+    r0.record(); ops.reconstruct(wd, Kd, sdd, mud, out=out); r1.record(); torch.cuda.synchronize()
+    rec_ms = r0.elapsed_time(r1)
+    t = torch.tensor([fac_ms, prd_ms, e2e_s * 1e3, rec_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fac_ms, prd_ms, e2e_ms, rec_ms = [float(x) for x in t.cpu()]
+    n_y = int(Kd.shape[1])
+    res = {
+        'metric': 'emulator_preds_per_s', 'unit': '(sample,design) pairs/s, all pu PCs',
+        'config': {'posterior_samples': nsamp, 'designs_per_gpu': npred, 'pu': PU, 'm': M, 'blocks_factored': nsamp * PU},
+        'value_pc_space': nsamp * npred * world / (prd_ms * 1e-3),
+        'value_pc_space_incl_factorisation': nsamp * npred * world / ((prd_ms + fac_ms) * 1e-3),
+        'factor_ms': fac_ms, 'predict_ms': prd_ms,
+        'predict_tflops_fp64': nsamp * PU * npred * (M * M + (3 * D + 2) * M) / (prd_ms * 1e-3) / 1e12,
+        'e2e': {'value': nsamp * 1024 * world / (e2e_ms * 1e-3), 'api': 'SepiaEmulatorPrediction(t_pred=1024 designs, samples, model)',
+                'note': 'host numpy in, realisations pred.w (nsamp,npred,pu) back on the host; includes factorisation'},
+        'reconstruct': {'rows': int(w32.shape[0]), 'n_y': n_y, 'ms': rec_ms, 'gbs': 4.0 * w32.shape[0] * n_y / rec_ms / 1e6,
+                        'frac_of_hbm_peak': 4.0 * w32.shape[0] * n_y / rec_ms / 1e6 / 6533.8},
+    }
+    if rank == 0:
+        # CPU baseline: SEPIA-style w_pred (fresh S22 solve per sample, PC and call), tiny sample
+        from oracle import sepia_oracle as so
+        num = so.OracleNum(model.data.sim_data.t_trans, model.data.sim_data.y_std[:, :64], np.asarray(sd_.K)[:, :64], resid_ss=0.0)
+        num.w = model._w_pcs.T.copy(); num.wv = num.w.reshape((-1, 1), order='F'); num.LamSim = model.num.LamSim
+        s2 = {k: v[:2] for k, v in samples.items()}
+        t0 = time.perf_counter()
+        so.w_pred(num, tp[:4], s2, rng=np.random.RandomState(0))
+        dt = time.perf_counter() - t0
+        res['cpu_baseline'] = {'value': 2 * 4 / dt, 'unit': res['unit'], 'kind': 'port', 'cores': blas_threads(),
+                               'sample': '2 samples x 4 designs in one SEPIA-style call (%.2f s)' % dt}
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -217,7 +288,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    out = eng.run(args.warmup, tb['step'], uniforms=us[:, :2 * P * args.warmup].contiguous(), record=False)
+    # clock spin-up after the long host-side set-up (the GPU has been idle), then the W contract warm-up steps
+    spin = torch.as_tensor(rs.random_sample((chains, 2 * P * 12))).to('cuda')
+    eng.run(12, tb['step'], uniforms=spin, record=False)
+    out = eng.run(args.warmup, tb['step'], uniforms=us[:, :2 * P * args.warmup].contiguous(), record=False, init_sigwl=False)
     us_t = us[:, 2 * P * args.warmup:].contiguous()
     theta0, sig0 = eng.theta.clone(), eng.sigwl.clone()
     barrier()
@@ -251,6 +325,9 @@ def run_ours(args):
     barrier()
     h2d = 2 * P * chains * 8
     d2h = (P + 1) * chains * 8 + 8 * chains / max(args.steps, 1)
+
+    # ---------------- second half of the metric: emulator predictions/s (cfg4 shape, bounded sample)
+    pred = prediction_bench(torch, model, args, rank, world)
 
     tm = torch.tensor([dev_ms, e2e_s * 1e3, sweep_ms, wos_ms], dtype=torch.float64, device='cuda')
     cnt = torch.tensor([float(n_valid)], dtype=torch.float64, device='cuda')
@@ -302,6 +379,7 @@ def run_ours(args):
                              'sample': '%d mcmc_steps of one chain in %.1f s (oracle/sepia_oracle.py, NumPy/SciPy FP64)'
                                        % (args.cpu_steps, cpu_dt)},
             'clocks': clocks,
+            'prediction': pred,
         }
         print(json.dumps(line))
     if world > 1:
@@ -311,7 +389,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--chains', type=int, default=59, help='independent chains per GPU (59*10 CTAs fill 148 SMs x 4 resident CTAs)')
@@ -320,6 +398,8 @@ def main():
     ap.add_argument('--ref-nx', type=int, default=400)
     ap.add_argument('--ref-nt', type=int, default=36)
     ap.add_argument('--cpu-steps', type=int, default=4)
+    ap.add_argument('--pred-samples', type=int, default=64)
+    ap.add_argument('--pred-designs', type=int, default=8192)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
