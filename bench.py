@@ -288,6 +288,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from here (spin-up + warm-up + timed region, all under load)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     # clock spin-up after the long host-side set-up (the GPU has been idle), then the W contract warm-up steps
     spin = torch.as_tensor(rs.random_sample((chains, 2 * P * 12))).to('cuda')
     eng.run(12, tb['step'], uniforms=spin, record=False)
@@ -295,9 +300,6 @@ def run_ours(args):
     us_t = us[:, 2 * P * args.warmup:].contiguous()
     theta0, sig0 = eng.theta.clone(), eng.sigwl.clone()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     out = eng.run(args.steps, tb['step'], uniforms=us_t, init_sigwl=False, record=True)
