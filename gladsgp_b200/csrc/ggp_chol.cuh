@@ -82,7 +82,8 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     EvalSmem s;
     double* p = reinterpret_cast<double*>(base);
     s.Minv = p;     p += 32 * MI_LD;
-    s.LT = p;       p += 32 * LT_LD;
+    s.LT = p;       p += 32 * LT_LD;     // LT and D are contiguous: outside the diagonal-block phase the two
+    s.D = p;        p += 32 * D_LD;      // serve as per-warp scratch of the covariance step (NWARP x 2 KB)
     s.rdiag = p;    p += 32;
     s.uj = p;       p += 32;
     s.red = p;      p += 8;
@@ -90,7 +91,6 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     s.wres = p;     p += Mp;
     s.SC = p;       p += (size_t)32 * ((d + 1) & ~1);
     s.sb = p;       p += ((d + 1) & ~1);
-    s.D = p;        p += 32 * D_LD;
     s.flag = reinterpret_cast<int*>(p);
     s.soff = s.flag + 4;
     return s;
@@ -160,11 +160,14 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
     const int pa_off = rb[pa_unit] * 8 + (lane & 3) * 16;
     const int pb_ks = lane >> 3;                                      // 8 lanes per sub-slab, 2 lines each
     const int pb_off = (row0 + 4 * (lane & 7)) * 8;
-    double2 an[NU];
+    double2 an[NU], bn[4];
     {
         const double* sl = a_slab(0);
 #pragma unroll
         for (int i = 0; i < NU; ++i) an[i] = ldcg2(sl + (rb[i] + g) * 8 + 2 * q);
+        const double* sb0 = Lb + soff[0];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) bn[cb] = *reinterpret_cast<const double2*>(sb0 + (row0 + 8 * cb + g) * 8 + 2 * q);
     }
     for (int kb = 0; kb < j; ++kb) {
         if (kb + PD < j) {
@@ -177,19 +180,20 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const int s = 4 * kb + ks;
-            const double* sl = Lb + soff[s];
-            double2 a[NU];
+            double2 a[NU], b[4];
 #pragma unroll
             for (int i = 0; i < NU; ++i) a[i] = an[i];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) b[cb] = bn[cb];
             if (ks < 3 || kb + 1 < j) {
                 const double* sn = a_slab(s + 1);
 #pragma unroll
                 for (int i = 0; i < NU; ++i) an[i] = ldcg2(sn + (rb[i] + g) * 8 + 2 * q);
-            }
-            double2 b[4];
+                const double* sbn = Lb + soff[s + 1];
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb)
-                b[cb] = *reinterpret_cast<const double2*>(sl + (row0 + 8 * cb + g) * 8 + 2 * q);
+                for (int cb = 0; cb < 4; ++cb)
+                    bn[cb] = *reinterpret_cast<const double2*>(sbn + (row0 + 8 * cb + g) * 8 + 2 * q);
+            }
             // all even-k DMMAs first, then the odd-k ones: dependent DMMAs on one accumulator are 4*NU apart
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
@@ -223,10 +227,13 @@ static __device__ __forceinline__ void unit_trsm(const double (&p)[4][2], double
 // Row coordinates come from global memory (Xr[r][d], L1/L2 resident) and are scaled by sqrt(beta) on the
 // fly -- the same expression that fills SC, so the two sides round identically; column coordinates of the
 // panel sit in shared memory (SC[k][32]).  self: rows are training points (diagonal / padding rules).
+// The eight exponentials go through a per-warp shared-memory scratch (scr[8][32]) so that the exp code exists
+// twice in the kernel instead of 32 times: the fully inlined version made the kernel > 100 KB of SASS and
+// instruction-fetch bound (profiles/README.md).
 static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double* __restrict__ Xr, int r, bool row_ok,
                                                 const double* __restrict__ SC, const double* __restrict__ sb, int d,
                                                 int m, int row0, int q, double inv_lamz, double diag, bool self,
-                                                const double* __restrict__ etab)
+                                                const double* __restrict__ etab, double* __restrict__ scr, int lane)
 {
     double dist[4][2];
 #pragma unroll
@@ -247,10 +254,17 @@ static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double*
     }
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) {
+        scr[(2 * cb) * 32 + lane] = -dist[cb][0];
+        scr[(2 * cb + 1) * 32 + lane] = -dist[cb][1];
+    }
+#pragma unroll 4
+    for (int e = 0; e < 8; ++e) scr[e * 32 + lane] = exp_neg(scr[e * 32 + lane], etab);
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int c = row0 + 8 * cb + 2 * q + e;
-            double v = (row_ok && c < m) ? exp_neg(-dist[cb][e], etab) * inv_lamz : 0.0;
+            double v = (row_ok && c < m) ? scr[(2 * cb + e) * 32 + lane] * inv_lamz : 0.0;
             if (self && r == c) v = (r < m) ? diag : 1.0;
             p[cb][e] = v - p[cb][e];
         }
@@ -294,7 +308,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
     __syncthreads();
 #ifdef GGP_PHASES
     unsigned long long tlast__ = clock64();
-    unsigned long long tserial__ = 0;
+    unsigned long long tserial__ = clock64();
 #endif
 
     for (int j = 0; j < nP; ++j) {
@@ -303,200 +317,201 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         double* __restrict__ Lpj = Lp + panel_off(j, Mp);
         const int nunits = Rj >> 3;
         // this warp owns units u = warp + NWARP*t (t = 0, 1, ...), processed two at a time; units 0..3 are the
-        // diagonal block (t = 0 of warps 0..3)
+        // diagonal block
         const int nmy = (nunits - warp + NWARP - 1) / NWARP;
+        const int npairs = max(1, (nmy + 1) >> 1);          // every warp runs pair 0 (it holds the barriers)
         fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
         __syncthreads();
         GGP_TICK(0);
+        double* __restrict__ scr = LT + warp * 256;          // per-warp scratch of the covariance step (LT is idle then)
+        static_assert(NWARP * 256 <= 32 * LT_LD, "covariance scratch must fit in LT");
 
-        // GEMM + covariance of the pair of units starting at t0: p = C - S in the accumulator layout
-        auto make_pair = [&](int t0, double (&acc)[2][4][2], int (&rb)[2]) -> int {
-            const int nu = min(2, nmy - t0);
+#pragma unroll 1
+        for (int pr = 0; pr < npairs; ++pr) {
+            const int t0 = 2 * pr;
+            const int nu = max(0, min(2, nmy - t0));
+            double acc[2][4][2];
+            int rb[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 rb[i] = row0 + 8 * (warp + NWARP * (t0 + ((i < nu) ? i : 0)));
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
             }
+            // ------------------------------------------------------------------ 1. DMMA update
+            GGP_TICKW(2, 23, acc[0][0][0]);
             if (j > 0) {
                 if (nu == 2) panel_gemm<2>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
                 else if (nu == 1) panel_gemm<1>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
             }
+            GGP_TICKW(2, 20, acc[0][0][0] + acc[1][3][1] + acc[0][3][1] + acc[1][0][0]);
+            // ------------------------------------------------------------------ 2. covariance, P = C - S (registers)
 #pragma unroll
             for (int i = 0; i < 2; ++i)
                 if (i < nu)
                     unit_cov(acc[i], X, rb[i] + g, rb[i] + g < m, sm.SC, sm.sb, d, m, row0, q, inv_lamz, diag, true,
-                             sm.etab);
-            return nu;
-        };
-        // X = P Minv^T for one unit, store to the packed factor, update the running forward solve of w
-        auto finish_unit = [&](const double (&pu)[4][2], int rbase) {
-            double xt[4][2];
-            unit_trsm(pu, xt, sm.Minv, g, q);
-            const int r = rbase + g;
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
-                const double2 u2 = *reinterpret_cast<const double2*>(sm.uj + 8 * cb + 2 * q);
-                s0 = fma(xt[cb][0], u2.x, s0);
-                s1 = fma(xt[cb][1], u2.y, s1);
-                *reinterpret_cast<double2*>(Lpj + (long long)cb * Rj * 8 + (long long)(r - row0) * 8 + 2 * q) =
-                    make_double2(xt[cb][0], xt[cb][1]);
-            }
-            double s = s0 + s1;
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (q == 0) sm.wres[r] -= s;
-        };
+                             sm.etab, scr, lane);
+            GGP_TICKW(2, 21, acc[0][0][0] + acc[1][3][1]);
 
-        // ---------------------------------------------------------------------- first pair (held across the
-        // diagonal-block phase in registers)
-        double acc0[2][4][2];
-        int rb0[2];
-        const int nu0 = make_pair(0, acc0, rb0);
-        GGP_TICK(1);
+            // ------------------------------------------------------------------ 3. diagonal block (first pair only)
+            if (pr == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int u = warp + NWARP * i;          // units 0..3 are the diagonal block
-            if (i < nu0 && u < 4) {
+                for (int i = 0; i < 2; ++i) {
+                    const int u = warp + NWARP * i;
+                    if (i < nu && u < 4) {
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb)
+                        for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        D[(8 * u + g) * D_LD + 8 * cb + 2 * q + e] = acc0[i][cb][e];
-            }
-        }
-        __syncthreads();                                                         // (A)
-        GGP_TICK(2);
-        if (warp == 0) {
-            // Cholesky of the 32x32 block, lane = row.  Columns are processed in blocks of 8 held in registers
-            // (pivots and multipliers move by shuffle); the trailing columns get one rank-8 update per block
-            // from shared memory instead of one read-modify-write per pivot.
-            double mypiv = 1.0;
-            int bad = 0;
-            GGP_TICKW(0, 9, D[lane * D_LD]);      // (slot 9: everything up to the start of the factorisation)
-#pragma unroll 1
-            for (int k0 = 0; k0 < 32 && !bad; k0 += 8) {
-                double x[8];
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) x[kk] = D[lane * D_LD + k0 + kk];
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const int k = k0 + kk;
-                    const double dk = __shfl_sync(0xffffffffu, x[kk], k);
-                    if (!(dk > 0.0) || !(dk < 1.0e300)) { if (!bad) bad = row0 + k + 1; }
-                    const double rk = rsqrt(dk);
-                    const double lik = (lane == k) ? dk * rk : x[kk] * rk;
-                    if (lane == k) mypiv = dk;
-                    x[kk] = lik;
-                    if (lane == 0) sm.rdiag[k] = rk;
-#pragma unroll
-                    for (int k2 = kk + 1; k2 < 8; ++k2)
-                        x[k2] = fma(-lik, __shfl_sync(0xffffffffu, lik, k0 + k2), x[k2]);
-                }
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const bool low = lane >= k0 + kk;
-                    D[lane * D_LD + k0 + kk] = low ? x[kk] : 0.0;
-                    LT[(k0 + kk) * LT_LD + lane] = low ? x[kk] : 0.0;
-                }
-                __syncwarp();
-#pragma unroll 2
-                for (int c = k0 + 8; c < 32; ++c) {
-                    double a = D[lane * D_LD + c];
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) a = fma(-x[kk], LT[(k0 + kk) * LT_LD + c], a);
-                    D[lane * D_LD + c] = a;
-                }
-                __syncwarp();
-            }
-            GGP_TICKW(0, 10, D[lane * D_LD + 31]);  // slot 10: factorisation
-            if (bad) { if (lane == 0) sm.flag[0] = bad; }
-            else logdet += 0.5 * log(mypiv);
-        }
-        GGP_TICK(3);
-        __syncthreads();                                                         // (B0)
-        GGP_TICK(4);
-        if (sm.flag[0] != 0) {
-            if (tid == 0 && info) *info = sm.flag[0];
-            return -INFINITY;
-        }
-        if (warp == 0) {
-            // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]
-            double b = sm.wres[row0 + lane];
-            GGP_TICKW(0, 11, b);                    // slot 11: factor end -> usolve start (barrier B0)
-            double myu = 0.0;
-#pragma unroll 1
-            for (int c = 0; c < 32; ++c) {
-                const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
-                if (lane == c) myu = uc;
-                if (lane > c) b = fma(-D[lane * D_LD + c], uc, b);
-            }
-            sm.uj[lane] = myu;
-            quad += myu * myu;
-            if (u_out) u_out[row0 + lane] = myu;
-            // store the diagonal rows of L (zeros above the diagonal)
-#pragma unroll 1
-            for (int ks = 0; ks < 4; ++ks) {
-                double* dst = Lpj + (long long)ks * Rj * 8 + (long long)lane * 8;
-#pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    const int cc = 8 * ks + c;
-                    *reinterpret_cast<double2*>(dst + c) =
-                        make_double2(cc > lane ? 0.0 : D[lane * D_LD + cc], cc + 1 > lane ? 0.0 : D[lane * D_LD + cc + 1]);
-                }
-            }
-            GGP_TICKW(0, 12, quad);                 // slot 12: usolve + diagonal row store
-        } else if (warp == 1) {
-            GGP_TICKW(1, 13, sm.rdiag[0]);          // slot 13: everything else for warp 1
-            // Minv = Ljj^-1: lane k solves Ljj y = e_k.  Rows in blocks of 8: the contribution of all earlier
-            // rows is accumulated for the 8 rows at once (one own-column load + four broadcast LDS.128 of
-            // LT[t][i0..i0+7] per t), then an 8x8 triangular solve in registers.
-            double* gm = Lp + minv_off(Mp) + 1024LL * j;
-#pragma unroll 1
-            for (int i0 = 0; i0 < 32; i0 += 8) {
-                double y[8];
-#pragma unroll
-                for (int ii = 0; ii < 8; ++ii) y[ii] = (i0 + ii == lane) ? 1.0 : 0.0;
-#pragma unroll 2
-                for (int t = 0; t < i0; ++t) {
-                    const double yt = sm.Minv[t * MI_LD + lane];
-                    const double* lt = LT + t * LT_LD + i0;              // L[i0+ii][t]
-#pragma unroll
-                    for (int ii = 0; ii < 8; ii += 2) {
-                        const double2 l2 = *reinterpret_cast<const double2*>(lt + ii);
-                        y[ii] = fma(-l2.x, yt, y[ii]);
-                        y[ii + 1] = fma(-l2.y, yt, y[ii + 1]);
+                            for (int e = 0; e < 2; ++e)
+                                D[(8 * u + g) * D_LD + 8 * cb + 2 * q + e] = acc[i][cb][e];
                     }
                 }
+                GGP_TICK(1);
+                __syncthreads();                                                 // (A)
+                GGP_TICK(2);
+                if (warp == 0) {
+                    // Cholesky of the 32x32 block, lane = row.  Columns in blocks of 8 held in registers; pivots and
+                    // multipliers are broadcast through shared memory (a double shuffle is ~25 SASS instructions
+                    // with its divergence fallback); trailing columns get one rank-8 update per block.
+                    double mypiv = 1.0;
+                    int bad = 0;
+                    GGP_TICKW(0, 9, D[lane * D_LD]);
+#pragma unroll 1
+                    for (int k0 = 0; k0 < 32; k0 += 8) {
+                        double x[8];
 #pragma unroll
-                for (int ii = 0; ii < 8; ++ii) {
-                    y[ii] *= sm.rdiag[i0 + ii];
+                        for (int kk = 0; kk < 8; ++kk) x[kk] = D[lane * D_LD + k0 + kk];
 #pragma unroll
-                    for (int i2 = ii + 1; i2 < 8; ++i2) y[i2] = fma(-LT[(i0 + ii) * LT_LD + i0 + i2], y[ii], y[i2]);
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const int k = k0 + kk;
+                            if (lane == k) sm.red[2] = x[kk];
+                            __syncwarp();
+                            const double dk = sm.red[2];
+                            if (!(dk > 0.0) || !(dk < 1.0e300)) { if (!bad) bad = row0 + k + 1; }
+                            const double rk = rsqrt(dk);
+                            const double lik = (lane == k) ? dk * rk : x[kk] * rk;
+                            if (lane == k) mypiv = dk;
+                            x[kk] = lik;
+                            if (lane == 0) sm.rdiag[k] = rk;
+                            LT[k * LT_LD + lane] = (lane >= k) ? lik : 0.0;
+                            __syncwarp();
+#pragma unroll
+                            for (int k2 = kk + 1; k2 < 8; ++k2) x[k2] = fma(-lik, LT[k * LT_LD + k0 + k2], x[k2]);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) D[lane * D_LD + k0 + kk] = (lane >= k0 + kk) ? x[kk] : 0.0;
+#pragma unroll 2
+                        for (int c = k0 + 8; c < 32; ++c) {
+                            double a = D[lane * D_LD + c];
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) a = fma(-x[kk], LT[(k0 + kk) * LT_LD + c], a);
+                            D[lane * D_LD + c] = a;
+                        }
+                        __syncwarp();
+                        if (bad) break;
+                    }
+                    GGP_TICKW(0, 10, D[lane * D_LD + 31]);
+                    if (bad) { if (lane == 0) sm.flag[0] = bad; }
+                    else logdet += 0.5 * log(mypiv);
                 }
-#pragma unroll
-                for (int ii = 0; ii < 8; ++ii) {
-                    sm.Minv[(i0 + ii) * MI_LD + lane] = y[ii];          // Minv[i][k = lane]
-                    gm[(i0 + ii) * 32 + lane] = y[ii];
+                GGP_TICK(3);
+                __syncthreads();                                                 // (B0)
+                GGP_TICK(4);
+                if (sm.flag[0] != 0) {
+                    if (tid == 0 && info) *info = sm.flag[0];
+                    return -INFINITY;
                 }
-                __syncwarp();
+                if (warp == 0) {
+                    // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]
+                    double b = sm.wres[row0 + lane];
+                    GGP_TICKW(0, 11, b);
+                    double myu = 0.0;
+#pragma unroll 1
+                    for (int c = 0; c < 32; ++c) {
+                        const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
+                        if (lane == c) myu = uc;
+                        if (lane > c) b = fma(-D[lane * D_LD + c], uc, b);
+                    }
+                    sm.uj[lane] = myu;
+                    quad += myu * myu;
+                    if (u_out) u_out[row0 + lane] = myu;
+                    // store the diagonal rows of L (zeros above the diagonal)
+#pragma unroll 1
+                    for (int ks = 0; ks < 4; ++ks) {
+                        double* dst = Lpj + (long long)ks * Rj * 8 + (long long)lane * 8;
+#pragma unroll
+                        for (int c = 0; c < 8; c += 2) {
+                            const int cc = 8 * ks + c;
+                            *reinterpret_cast<double2*>(dst + c) = make_double2(D[lane * D_LD + cc], D[lane * D_LD + cc + 1]);
+                        }
+                    }
+                    GGP_TICKW(0, 12, quad);
+                } else if (warp == 1) {
+                    // Minv = Ljj^-1: lane k solves Ljj y = e_k.  Rows in blocks of 8: the contribution of all earlier
+                    // rows is accumulated for the 8 rows at once (one own-column load + four broadcast LDS.128 of
+                    // LT[t][i0..i0+7] per t), then an 8x8 triangular solve in registers.
+                    GGP_TICKW(1, 13, sm.rdiag[0]);
+                    double* gm = Lp + minv_off(Mp) + 1024LL * j;
+#pragma unroll 1
+                    for (int i0 = 0; i0 < 32; i0 += 8) {
+                        double y[8];
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) y[ii] = (i0 + ii == lane) ? 1.0 : 0.0;
+#pragma unroll 2
+                        for (int t = 0; t < i0; ++t) {
+                            const double yt = sm.Minv[t * MI_LD + lane];
+                            const double* lt = LT + t * LT_LD + i0;              // L[i0+ii][t]
+#pragma unroll
+                            for (int ii = 0; ii < 8; ii += 2) {
+                                const double2 l2 = *reinterpret_cast<const double2*>(lt + ii);
+                                y[ii] = fma(-l2.x, yt, y[ii]);
+                                y[ii + 1] = fma(-l2.y, yt, y[ii + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            y[ii] *= sm.rdiag[i0 + ii];
+#pragma unroll
+                            for (int i2 = ii + 1; i2 < 8; ++i2) y[i2] = fma(-LT[(i0 + ii) * LT_LD + i0 + i2], y[ii], y[i2]);
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            sm.Minv[(i0 + ii) * MI_LD + lane] = y[ii];          // Minv[i][k = lane]
+                            gm[(i0 + ii) * 32 + lane] = y[ii];
+                        }
+                        __syncwarp();
+                    }
+                    GGP_TICKW(1, 14, sm.Minv[lane]);
+                }
+                GGP_TICK(5);
+                __syncthreads();                                                 // (B)
+                GGP_TICK(6);
             }
-            GGP_TICKW(1, 14, sm.Minv[lane]);        // slot 14: Minv
-        }
-        GGP_TICK(5);
-        __syncthreads();                                                         // (B)
-        GGP_TICK(6);
 
-        // ---------------------------------------------------------------------- finish the held pair, then the rest
-        if (nu0 >= 1 && warp >= 4) finish_unit(acc0[0], rb0[0]);                 // units 0..3 are the diagonal block
-        if (nu0 >= 2 && warp + NWARP >= 4) finish_unit(acc0[1], rb0[1]);
-        for (int t0 = 2; t0 < nmy; t0 += 2) {
-            double acc[2][4][2];
-            int rb[2];
-            const int nu = make_pair(t0, acc, rb);
-            finish_unit(acc[0], rb[0]);
-            if (nu >= 2) finish_unit(acc[1], rb[1]);
+            // ------------------------------------------------------------------ 4. X = P Minv^T, store, update w
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i < nu && !(pr == 0 && warp + NWARP * i < 4)) {
+                    GGP_TICKW(2, 23, acc[i][0][0]);
+                    double xt[4][2];
+                    unit_trsm(acc[i], xt, sm.Minv, g, q);
+                    const int r = rb[i] + g;
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        const double2 u2 = *reinterpret_cast<const double2*>(sm.uj + 8 * cb + 2 * q);
+                        s0 = fma(xt[cb][0], u2.x, s0);
+                        s1 = fma(xt[cb][1], u2.y, s1);
+                        *reinterpret_cast<double2*>(Lpj + (long long)cb * Rj * 8 + (long long)(r - row0) * 8 + 2 * q) =
+                            make_double2(xt[cb][0], xt[cb][1]);
+                    }
+                    double sdot = s0 + s1;
+                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+                    if (q == 0) sm.wres[r] -= sdot;
+                    GGP_TICKW(2, 22, sdot);
+                }
+            }
         }
         GGP_TICK(7);
         __syncthreads();                                                         // (C)

@@ -25,10 +25,11 @@ struct PredSmem {
     double* etab;   // [32]
     double* sb;     // [d]
     double* SC;     // [d][32] scaled training coordinates of the current panel
+    double* scr;    // [PNW][8][32] per-warp scratch of the covariance step
 };
 
 __host__ __device__ inline size_t pred_smem_bytes(int d) {
-    return (size_t)(32 * MI_LD + 32 + 32 + 34 * ((d + 1) & ~1)) * sizeof(double);
+    return (size_t)(32 * MI_LD + 32 + 32 + 34 * ((d + 1) & ~1) + PNW * 256) * sizeof(double);
 }
 
 // One CTA pushes blocks of PB test designs through the cached factor of block b.  Rows = designs: each
@@ -50,7 +51,8 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
         sm.uj = p;    p += 32;
         sm.etab = p;  p += 32;
         sm.SC = p;    p += 32 * ((d + 1) & ~1);
-        sm.sb = p;
+        sm.sb = p;    p += ((d + 1) & ~1);
+        sm.scr = p;
     }
     __shared__ int soff[1024];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,7 +100,7 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
                 for (int i = 0; i < 2; ++i) {
                     const int r = rb[i] + g;                       // local design index
                     unit_cov(acc[i], Xp + (size_t)t0 * d, r, r < nt, sm.SC, sm.sb, d, m, row0, q, inv_lamz, 0.0, false,
-                             sm.etab);
+                             sm.etab, sm.scr + warp * 256, lane);
                     double xt[4][2];
                     unit_trsm(acc[i], xt, sm.Minv, g, q);
                     double s0 = 0.0, q0 = 0.0;

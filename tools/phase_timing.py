@@ -32,7 +32,11 @@ names = ['fill+sync', 'pair0 gemm+cov', 'wait A', 'factor(w0)/idle', 'wait B0', 
 print('precise (data-dependent) serial timers, cycles per panel (16 panels):')
 for slot, n in ((9, 'w0: other'), (15, 'w0: factor blk0'), (10, 'w0: factor blk1-3'), (11, 'w0: B0 barrier'), (12, 'w0: usolve+store'), (13, 'w1: other'), (14, 'w1: Minv')):
     print('   %-20s %9.0f' % (n, buf[slot] / 16.0))
-for w, off in (('warp0', 0), ('warp7', 16)):
+tot2 = sum(buf[i] for i in (20, 21, 22, 23))
+print('worker warp 2 of block 0: total', tot2)
+for slot, n in ((20, 'DMMA update'), (21, 'covariance'), (22, 'TRSM+store'), (23, 'other (barriers, serial wait)')):
+    print('   %-30s %10d %5.1f%%' % (n, buf[slot], 100.0 * buf[slot] / max(tot2, 1)))
+for w, off in (('warp0', 0),):
     tot = sum(buf[off + i] for i in range(9))
     print(w, 'total cycles', tot)
     for i, n in enumerate(names):
