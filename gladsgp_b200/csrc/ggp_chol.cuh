@@ -223,52 +223,70 @@ static __device__ __forceinline__ void unit_trsm(const double (&p)[4][2], double
     }
 }
 
-// Covariance entries of one unit (8 rows x 32 panel columns) in the accumulator layout: p = C - p.
+// Covariance entries of NU units (8 rows x 32 panel columns each) in the accumulator layout: p = C - p.
 // Row coordinates come from global memory (Xr[r][d], L1/L2 resident) and are scaled by sqrt(beta) on the
 // fly -- the same expression that fills SC, so the two sides round identically; column coordinates of the
-// panel sit in shared memory (SC[k][32]).  self: rows are training points (diagonal / padding rules).
-// The eight exponentials go through a per-warp shared-memory scratch (scr[8][32]) so that the exp code exists
-// twice in the kernel instead of 32 times: the fully inlined version made the kernel > 100 KB of SASS and
-// instruction-fetch bound (profiles/README.md).
-static __device__ __forceinline__ void unit_cov(double (&p)[4][2], const double* __restrict__ Xr, int r, bool row_ok,
-                                                const double* __restrict__ SC, const double* __restrict__ sb, int d,
-                                                int m, int row0, int q, double inv_lamz, double diag, bool self,
+// panel sit in shared memory (SC[k][32]) and are shared by the NU units.  self: rows are training points
+// (diagonal / padding rules).  The 8*NU exponentials go through a per-warp shared-memory scratch
+// (scr[16][32]) and a 4-way unrolled loop, so the exp code exists 4 times in the kernel instead of 32: the
+// fully inlined version made the kernel > 100 KB of SASS and instruction-fetch bound (profiles/README.md).
+template <int NU>
+static __device__ __forceinline__ void pair_cov(double (&p)[2][4][2], const double* __restrict__ Xr, const int (&r)[2],
+                                                const bool (&row_ok)[2], const double* __restrict__ SC,
+                                                const double* __restrict__ sb, int d, int m, int row0, int q,
+                                                double inv_lamz, double diag, bool self,
                                                 const double* __restrict__ etab, double* __restrict__ scr, int lane)
 {
-    double dist[4][2];
+    double dist[NU][4][2];
+    const double* xr[NU];
+    double xnext[NU];
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) { dist[cb][0] = 0.0; dist[cb][1] = 0.0; }
-    const double* xr = Xr + (size_t)(row_ok ? r : 0) * d;
-    double xnext = __ldg(xr);
+    for (int i = 0; i < NU; ++i) {
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) { dist[i][cb][0] = 0.0; dist[i][cb][1] = 0.0; }
+        xr[i] = Xr + (size_t)(row_ok[i] ? r[i] : 0) * d;
+        xnext[i] = __ldg(xr[i]);
+    }
     for (int k = 0; k < d; ++k) {
-        const double sr = xnext * sb[k];
-        if (k + 1 < d) xnext = __ldg(xr + k + 1);
+        double sr[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            sr[i] = xnext[i] * sb[k];
+            if (k + 1 < d) xnext[i] = __ldg(xr[i] + k + 1);
+        }
         const double* sc = SC + k * 32 + 2 * q;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
             const double2 c2 = *reinterpret_cast<const double2*>(sc + 8 * cb);
-            const double t0 = sr - c2.x, t1 = sr - c2.y;
-            dist[cb][0] = fma(t0, t0, dist[cb][0]);
-            dist[cb][1] = fma(t1, t1, dist[cb][1]);
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const double t0 = sr[i] - c2.x, t1 = sr[i] - c2.y;
+                dist[i][cb][0] = fma(t0, t0, dist[i][cb][0]);
+                dist[i][cb][1] = fma(t1, t1, dist[i][cb][1]);
+            }
         }
     }
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
-        scr[(2 * cb) * 32 + lane] = -dist[cb][0];
-        scr[(2 * cb + 1) * 32 + lane] = -dist[cb][1];
-    }
+    for (int i = 0; i < NU; ++i)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            scr[(8 * i + 2 * cb) * 32 + lane] = -dist[i][cb][0];
+            scr[(8 * i + 2 * cb + 1) * 32 + lane] = -dist[i][cb][1];
+        }
 #pragma unroll 4
-    for (int e = 0; e < 8; ++e) scr[e * 32 + lane] = exp_neg(scr[e * 32 + lane], etab);
+    for (int e = 0; e < 8 * NU; ++e) scr[e * 32 + lane] = exp_neg(scr[e * 32 + lane], etab);
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int i = 0; i < NU; ++i)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int c = row0 + 8 * cb + 2 * q + e;
-            double v = (row_ok && c < m) ? scr[(2 * cb + e) * 32 + lane] * inv_lamz : 0.0;
-            if (self && r == c) v = (r < m) ? diag : 1.0;
-            p[cb][e] = v - p[cb][e];
+        for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = row0 + 8 * cb + 2 * q + e;
+                double v = (row_ok[i] && c < m) ? scr[(8 * i + 2 * cb + e) * 32 + lane] * inv_lamz : 0.0;
+                if (self && r[i] == c) v = (r[i] < m) ? diag : 1.0;
+                p[i][cb][e] = v - p[i][cb][e];
+            }
         }
-    }
 }
 
 // scaled coordinates of the 32 columns of panel `row0` -> SC[k][32]; all threads, caller syncs
@@ -323,8 +341,8 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
         __syncthreads();
         GGP_TICK(0);
-        double* __restrict__ scr = LT + warp * 256;          // per-warp scratch of the covariance step (LT is idle then)
-        static_assert(NWARP * 256 <= 32 * LT_LD, "covariance scratch must fit in LT");
+        double* __restrict__ scr = LT + warp * 512;          // per-warp scratch of the covariance step (LT and D are idle then)
+        static_assert(NWARP * 512 <= 32 * LT_LD + 32 * D_LD, "covariance scratch must fit in LT + D");
 
 #pragma unroll 1
         for (int pr = 0; pr < npairs; ++pr) {
@@ -346,15 +364,17 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
             }
             GGP_TICKW(2, 20, acc[0][0][0] + acc[1][3][1] + acc[0][3][1] + acc[1][0][0]);
             // ------------------------------------------------------------------ 2. covariance, P = C - S (registers)
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-                if (i < nu)
-                    unit_cov(acc[i], X, rb[i] + g, rb[i] + g < m, sm.SC, sm.sb, d, m, row0, q, inv_lamz, diag, true,
-                             sm.etab, scr, lane);
+            {
+                const int rr[2] = {rb[0] + g, rb[1] + g};
+                const bool ok[2] = {rr[0] < m, rr[1] < m};
+                if (nu == 2) pair_cov<2>(acc, X, rr, ok, sm.SC, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane);
+                else if (nu == 1) pair_cov<1>(acc, X, rr, ok, sm.SC, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane);
+            }
             GGP_TICKW(2, 21, acc[0][0][0] + acc[1][3][1]);
 
             // ------------------------------------------------------------------ 3. diagonal block (first pair only)
             if (pr == 0) {
+                __syncthreads();          // every warp is done with its covariance scratch (it aliases D)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int u = warp + NWARP * i;

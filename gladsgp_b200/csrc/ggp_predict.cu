@@ -25,11 +25,11 @@ struct PredSmem {
     double* etab;   // [32]
     double* sb;     // [d]
     double* SC;     // [d][32] scaled training coordinates of the current panel
-    double* scr;    // [PNW][8][32] per-warp scratch of the covariance step
+    double* scr;    // [PNW][16][32] per-warp scratch of the covariance step
 };
 
 __host__ __device__ inline size_t pred_smem_bytes(int d) {
-    return (size_t)(32 * MI_LD + 32 + 32 + 34 * ((d + 1) & ~1) + PNW * 256) * sizeof(double);
+    return (size_t)(32 * MI_LD + 32 + 32 + 34 * ((d + 1) & ~1) + PNW * 512) * sizeof(double);
 }
 
 // One CTA pushes blocks of PB test designs through the cached factor of block b.  Rows = designs: each
@@ -96,11 +96,15 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
                     for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
                 }
                 if (j > 0) panel_gemm<2>(acc, Vw, Lp, soff, j, row0, rb, g, q, PB);
+                {
+                    const int rr[2] = {rb[0] + g, rb[1] + g};
+                    const bool ok[2] = {rr[0] < nt, rr[1] < nt};
+                    pair_cov<2>(acc, Xp + (size_t)t0 * d, rr, ok, sm.SC, sm.sb, d, m, row0, q, inv_lamz, 0.0, false, sm.etab,
+                                sm.scr + warp * 512, lane);
+                }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int r = rb[i] + g;                       // local design index
-                    unit_cov(acc[i], Xp + (size_t)t0 * d, r, r < nt, sm.SC, sm.sb, d, m, row0, q, inv_lamz, 0.0, false,
-                             sm.etab, sm.scr + warp * 256, lane);
                     double xt[4][2];
                     unit_trsm(acc[i], xt, sm.Minv, g, q);
                     double s0 = 0.0, q0 = 0.0;
