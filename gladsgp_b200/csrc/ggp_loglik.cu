@@ -14,15 +14,16 @@ namespace ggp {
 // ---------------------------------------------------------------------------------------------
 constexpr int CT = 64;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 cov_build_kernel(const double* __restrict__ X, int m, int d, const double* __restrict__ beta,
                  const double* __restrict__ lamz, const double* __restrict__ diag_add,
                  double* __restrict__ C, int ntile)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* Sr = reinterpret_cast<double*>(smem_raw);      // [CT][d]
-    double* Sc = Sr + CT * d;                              // [CT][d]
-    double* T = Sc + CT * d;                               // [CT][CT+1]
+    double* Sr = reinterpret_cast<double*>(smem_raw);      // [d][CT] scaled row coordinates (transposed)
+    double* Sc = Sr + CT * d;                              // [d][CT] scaled column coordinates
+    double* T = Sc + CT * d;                               // [CT][CT+1] transposed tile
+    double* etab = T + CT * (CT + 1);                      // [32]
     const int b = blockIdx.y;
     // decode lower-triangular tile index
     int t = blockIdx.x;
@@ -34,37 +35,58 @@ cov_build_kernel(const double* __restrict__ X, int m, int d, const double* __res
     const double il = 1.0 / lamz[b];
     const double dg = il + diag_add[b];
     const int r0 = bi * CT, c0 = bj * CT;
+    fill_exp_table(etab);
     for (int idx = threadIdx.x; idx < CT * d; idx += blockDim.x) {
-        int r = idx / d, k = idx - r * d;
-        double sb = sqrt(be[k]);
+        const int k = idx / CT, r = idx - k * CT;
+        const double sb = sqrt(be[k]);
         Sr[idx] = (r0 + r < m) ? X[(size_t)(r0 + r) * d + k] * sb : 0.0;
         Sc[idx] = (c0 + r < m) ? X[(size_t)(c0 + r) * d + k] * sb : 0.0;
     }
     __syncthreads();
     double* Cb = C + (size_t)b * m * m;
-    // each thread: 4 rows x 4 cols
+    const bool vec2 = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    // each thread: 4 rows (ty + 16 i) x 4 consecutive columns (4 tx + j), distances in registers
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    for (int rr = 0; rr < 4; ++rr) {
-        const int lr = ty + 16 * rr;
+    double dist[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dist[i][j] = 0.0;
+    for (int k = 0; k < d; ++k) {
+        double rv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rv[i] = Sr[k * CT + ty + 16 * i];
+        const double2 c01 = *reinterpret_cast<const double2*>(Sc + k * CT + 4 * tx);
+        const double2 c23 = *reinterpret_cast<const double2*>(Sc + k * CT + 4 * tx + 2);
+        const double cv[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double df = rv[i] - cv[j];
+                dist[i][j] = fma(df, df, dist[i][j]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int lr = ty + 16 * i;
         const int r = r0 + lr;
         double v[4];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int lc = 4 * tx + cc;
-            const int c = c0 + lc;
-            double dist = 0.0;
-            for (int k = 0; k < d; ++k) {
-                double df = Sr[lr * d + k] - Sc[lc * d + k];
-                dist = fma(df, df, dist);
-            }
-            v[cc] = (r == c) ? dg : exp(-dist) * il;
-            T[lc * (CT + 1) + lr] = v[cc];
+        for (int j = 0; j < 4; ++j) {
+            const int lc = 4 * tx + j;
+            v[j] = (r == c0 + lc) ? dg : exp_neg(-dist[i][j], etab) * il;
+            T[lc * (CT + 1) + lr] = v[j];
         }
         if (r < m) {
+            const int c = c0 + 4 * tx;
+            if (vec2 && c + 3 < m) {
+                __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c), make_double2(v[0], v[1]));
+                __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c + 2), make_double2(v[2], v[3]));
+            } else {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = c0 + 4 * tx + cc;
-                if (c < m) Cb[(size_t)r * m + c] = v[cc];
+                for (int j = 0; j < 4; ++j)
+                    if (c + j < m) Cb[(size_t)r * m + c + j] = v[j];
             }
         }
     }
@@ -74,10 +96,15 @@ cov_build_kernel(const double* __restrict__ X, int m, int d, const double* __res
             const int lr = ty + 16 * rr;          // row of the transposed tile = column of the original
             const int r = c0 + lr;
             if (r < m) {
+                const int c = r0 + 4 * tx;
+                const double* tp = T + lr * (CT + 1) + 4 * tx;
+                if (vec2 && c + 3 < m) {
+                    __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c), make_double2(tp[0], tp[1]));
+                    __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c + 2), make_double2(tp[2], tp[3]));
+                } else {
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int c = r0 + 4 * tx + cc;
-                    if (c < m) Cb[(size_t)r * m + c] = T[lr * (CT + 1) + 4 * tx + cc];
+                    for (int cc = 0; cc < 4; ++cc)
+                        if (c + cc < m) Cb[(size_t)r * m + c + cc] = tp[cc];
                 }
             }
         }
@@ -185,7 +212,7 @@ int ggp_cov_build_f64(const double* X, int m, int d, const double* beta, const d
     cudaStream_t st = (cudaStream_t)stream;
     int nt = (m + CT - 1) / CT;
     int ntile = nt * (nt + 1) / 2;
-    size_t smem = (size_t)(2 * CT * d + CT * (CT + 1)) * sizeof(double);
+    size_t smem = (size_t)(2 * CT * d + CT * (CT + 1) + 32) * sizeof(double);
     GGP_ARG(smem <= 200 * 1024, "d too large for cov_build");
     GGP_CUDA(cudaFuncSetAttribute(cov_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cov_build_kernel<<<dim3(ntile, B), 256, smem, st>>>(X, m, d, beta, lamz, diag_add, C_out, ntile);
