@@ -21,64 +21,78 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_CPL = 4;                 // columns per lane
 constexpr int RS_CHUNK = 32 * RS_CPL;     // columns per warp chunk
 
-// ---- Y = X * Omega : CTA owns column chunks, accumulates Y in shared memory ---------------------
-template <int RG>
-__global__ void __launch_bounds__(RS_THREADS, 1)
+// ---- Y = X * Omega : the CTA streams 32-column chunks of all m rows through a padded shared-memory tile
+// (coalesced 128-byte row segments in, conflict-free column reads out); each thread owns RPT rows and keeps
+// their RG partial outputs in registers, Omega rows are broadcast LDS.128.  FMA-bound at ~20 B/clk/SM.
+constexpr int SK_CK = 32;
+
+template <int RG, int RPT>
+__global__ void __launch_bounds__(RS_THREADS, 2)
 sketch_kernel(const float* __restrict__ X, int m, long long n, const float* __restrict__ OmT, int r, int k0,
               float* __restrict__ partial)
 {
+    constexpr int RGP = (RG + 3) & ~3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* Ys = reinterpret_cast<float*>(smem_raw);          // [m][32]
+    float* Xs = reinterpret_cast<float*>(smem_raw);                 // [RPT*256][33]
+    float* Os = Xs + (size_t)RPT * RS_THREADS * 33;                 // [32][RGP]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < m * 32; idx += RS_THREADS) Ys[idx] = 0.f;
-    __syncthreads();
-    const long long nchunk = (n + RS_CHUNK - 1) / RS_CHUNK;
+    float acc[RPT][RGP];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int k = 0; k < RGP; ++k) acc[i][k] = 0.f;
+    const int mrows = RPT * RS_THREADS;                             // padded row count handled by the CTA
+    const long long nchunk = (n + SK_CK - 1) / SK_CK;
     for (long long ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
-        const long long c0 = ch * RS_CHUNK;
-        float om[RS_CPL][RG];
-        bool inb[RS_CPL];
+        const long long c0 = ch * SK_CK;
+        const bool cin = c0 + lane < n;
+        __syncthreads();                                            // previous chunk consumed
+        // tile load: warp w takes rows w, w+8, ...; 16 loads in flight per thread
+        for (int rb = warp; rb < mrows; rb += RS_WARPS * 16) {
+            float v[16];
 #pragma unroll
-        for (int i = 0; i < RS_CPL; ++i) {
-            const long long c = c0 + lane + 32 * i;
-            inb[i] = c < n;
+            for (int u = 0; u < 16; ++u) {
+                const int row = rb + RS_WARPS * u;
+                v[u] = (row < m && cin) ? __ldcs(X + (size_t)row * n + c0 + lane) : 0.f;
+            }
 #pragma unroll
-            for (int k = 0; k < RG; ++k)
-                om[i][k] = (inb[i] && k0 + k < r) ? OmT[(size_t)(k0 + k) * n + c] : 0.f;
+            for (int u = 0; u < 16; ++u) {
+                const int row = rb + RS_WARPS * u;
+                if (row < mrows) Xs[row * 33 + lane] = v[u];
+            }
         }
-        for (int row = warp; row < m; row += RS_WARPS) {
-            const float* xr = X + (size_t)row * n + c0 + lane;
-            float x[RS_CPL];
+        for (int idx = tid; idx < RGP * 32; idx += RS_THREADS) {
+            const int k = idx >> 5, c = idx & 31;
+            Os[c * RGP + k] = (k < RG && k0 + k < r && c0 + c < n) ? OmT[(size_t)(k0 + k) * n + c0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int c = 0; c < SK_CK; ++c) {
+            float x[RPT];
 #pragma unroll
-            for (int i = 0; i < RS_CPL; ++i) x[i] = inb[i] ? __ldcs(xr + 32 * i) : 0.f;
-            float v[32];
+            for (int i = 0; i < RPT; ++i) x[i] = Xs[(tid + RS_THREADS * i) * 33 + c];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (k < RG) {
-                    float s = x[0] * om[0][k];
+            for (int k4 = 0; k4 < RGP; k4 += 4) {
+                const float4 o4 = *reinterpret_cast<const float4*>(Os + c * RGP + k4);
 #pragma unroll
-                    for (int i = 1; i < RS_CPL; ++i) s = fmaf(x[i], om[i][k], s);
-                    v[k] = s;
-                } else {
-                    v[k] = 0.f;
+                for (int i = 0; i < RPT; ++i) {
+                    acc[i][k4 + 0] = fmaf(x[i], o4.x, acc[i][k4 + 0]);
+                    acc[i][k4 + 1] = fmaf(x[i], o4.y, acc[i][k4 + 1]);
+                    acc[i][k4 + 2] = fmaf(x[i], o4.z, acc[i][k4 + 2]);
+                    acc[i][k4 + 3] = fmaf(x[i], o4.w, acc[i][k4 + 3]);
                 }
             }
-            // transpose-reduce: after the 5 rounds lane l holds sum over lanes of v[l]
-#pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const bool up = (lane & step) != 0;
-#pragma unroll
-                for (int j = 0; j < step; ++j) {
-                    const float send = up ? v[j] : v[j + step];
-                    const float keep = up ? v[j + step] : v[j];
-                    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-                }
-            }
-            Ys[row * 32 + lane] += v[0];       // rows are warp-private: no race
         }
     }
-    __syncthreads();
     float* out = partial + (size_t)blockIdx.x * m * 32;
-    for (int idx = tid; idx < m * 32; idx += RS_THREADS) out[idx] = Ys[idx];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int row = tid + RS_THREADS * i;
+        if (row < m) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) out[row * 32 + k] = (k < RG) ? acc[i][k < RGP ? k : 0] : 0.f;
+        }
+    }
 }
 
 __global__ void sketch_reduce_kernel(const float* __restrict__ partial, int nparts, int m, int r, int k0,
@@ -120,7 +134,7 @@ xty_kernel(const float* __restrict__ X, int m, long long n, const float* __restr
 #pragma unroll
             for (int k = 0; k < RGP; ++k) acc[i][k] = 0.f;
         const float* xc = X + c0 + lane;
-#pragma unroll 2
+#pragma unroll 8
         for (int row = 0; row < m; ++row) {
             const float* xr = xc + (size_t)row * n;
             float x[RS_CPL];
@@ -161,12 +175,24 @@ static int sm_count()
 
 using namespace ggp;
 
+template <int RG, int RPT>
+static int launch_sketch(const float* X, int m, long long n, const float* OmT, int r, int k0, float* partial, int grid,
+                         cudaStream_t st)
+{
+    constexpr int RGP = (RG + 3) & ~3;
+    const size_t smem = ((size_t)RPT * RS_THREADS * 33 + 32 * RGP) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(sketch_kernel<RG, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sketch_kernel)");
+    sketch_kernel<RG, RPT><<<grid, RS_THREADS, smem, st>>>(X, m, n, OmT, r, k0, partial);
+    return GGP_OK;
+}
+
 extern "C" {
 
 long long ggp_rsvd_workspace_bytes(int m)
 {
     if (m <= 0) return -1;
-    return (long long)sm_count() * m * 32 * (long long)sizeof(float);
+    return 2LL * sm_count() * m * 32 * (long long)sizeof(float);
 }
 
 int ggp_rsvd_sketch_f32(const float* X, int m, long long n, const float* OmegaT, int r, float* Y_out,
@@ -174,26 +200,28 @@ int ggp_rsvd_sketch_f32(const float* X, int m, long long n, const float* OmegaT,
 {
     GGP_ARG(X && OmegaT && Y_out && workspace, "null pointer");
     GGP_ARG(m > 0 && n > 0 && r > 0, "m, n, r must be positive");
-    const size_t smem = (size_t)m * 32 * sizeof(float);
-    if (smem > 200 * 1024) {
-        set_error("ggp_rsvd_sketch_f32: m=%d too large (needs %zu B shared memory)", m, smem);
+    if (m > 4 * RS_THREADS) {
+        set_error("ggp_rsvd_sketch_f32: m=%d > %d not supported", m, 4 * RS_THREADS);
         return GGP_ERR_UNSUPPORTED;
     }
-    const int grid = sm_count();
+    const int grid = 2 * sm_count();
     if (workspace_bytes < ggp_rsvd_workspace_bytes(m)) {
         set_error("ggp_rsvd_sketch_f32: workspace too small");
         return GGP_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
     float* partial = reinterpret_cast<float*>(workspace);
+    const int rpt = (m + RS_THREADS - 1) / RS_THREADS;
     for (int k0 = 0; k0 < r; k0 += 32) {
-        if (r - k0 <= 25) {
-            GGP_CUDA(cudaFuncSetAttribute(sketch_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sketch_kernel<25><<<grid, RS_THREADS, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
-        } else {
-            GGP_CUDA(cudaFuncSetAttribute(sketch_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sketch_kernel<32><<<grid, RS_THREADS, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
-        }
+        const bool small = (r - k0 <= 25);
+        int rc;
+        if (rpt <= 1) rc = small ? launch_sketch<25, 1>(X, m, n, OmegaT, r, k0, partial, grid, st)
+                                 : launch_sketch<32, 1>(X, m, n, OmegaT, r, k0, partial, grid, st);
+        else if (rpt == 2) rc = small ? launch_sketch<25, 2>(X, m, n, OmegaT, r, k0, partial, grid, st)
+                                      : launch_sketch<32, 2>(X, m, n, OmegaT, r, k0, partial, grid, st);
+        else rc = small ? launch_sketch<25, 4>(X, m, n, OmegaT, r, k0, partial, grid, st)
+                        : launch_sketch<32, 4>(X, m, n, OmegaT, r, k0, partial, grid, st);
+        if (rc != GGP_OK) return rc;
         sketch_reduce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(partial, grid, m, r, k0, Y_out);
     }
     GGP_CUDA(cudaGetLastError());
