@@ -22,6 +22,7 @@
 // over shared memory: a fully unrolled register version made the kernel 200 KB of SASS and
 // instruction-fetch bound (profiles/r1b_*).
 #pragma once
+#include <cstdlib>
 #include "ggp_common.cuh"
 
 namespace ggp {
@@ -303,12 +304,22 @@ static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SC
 // *info (if non-null, written by thread 0) = 0 or 1-based index of the failing pivot.
 // beta may point to global or shared memory.  Lp is the packed-factor workspace (packed_doubles(Mp)).
 // u_out (nullable): receives L^-1 w (Mp entries, zero padded).
+// CL = true: the matrix is shared by the CTAs of a thread-block cluster (cluster size G = %cluster_nctarank):
+// 8-row units are dealt round-robin to the G*NWARP warps, CTA 0 owns the diagonal block and publishes Minv / u
+// through global memory, panels are separated by cluster barriers (release/acquire), the running forward solve
+// of w lives in global memory.  Only CTA 0 returns the value.
+template <bool CL = false>
 static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, const double* __restrict__ X, int m, int Mp, int d,
                                     const double* beta, double lamz, double diag_add,
                                     const double* __restrict__ w, double* __restrict__ Lp,
                                     double* __restrict__ u_out, int* info)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int crank = CL ? (int)cluster_ctarank() : 0;
+    const int G = CL ? (int)cluster_nctarank() : 1;
+    const int gw = crank * NWARP + warp, TW = G * NWARP;       // warp index / warp count over the cluster
+    double* __restrict__ aux = Lp + aux_off(Mp);               // [Mp] wres, [32] u block, [32] flag (cluster variant)
+    double* __restrict__ wres = CL ? aux : sm.wres;
     const int g = lane >> 2, q = lane & 3;
     const int nP = Mp >> 5;
     const double inv_lamz = 1.0 / lamz;
@@ -316,9 +327,11 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
     double* __restrict__ D = sm.D;
     double* __restrict__ LT = sm.LT;
 
+    if (CL) cluster_sync_all();   // previous evaluation (and the caller's state update) finished cluster-wide
     __syncthreads();   // previous user of the shared buffers is done
     if (tid < d) sm.sb[tid] = sqrt(beta[tid]);
-    for (int r = tid; r < Mp; r += NT) sm.wres[r] = (r < m) ? w[r] : 0.0;
+    for (int r = crank * NT + tid; r < Mp; r += G * NT) wres[r] = (r < m) ? w[r] : 0.0;
+    if (CL && crank == 0 && tid == 0) aux[Mp + 32] = 0.0;
     fill_exp_table(sm.etab);
     fill_slab_offsets(sm.soff, Mp);
     if (tid == 0) sm.flag[0] = 0;
@@ -336,8 +349,9 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         const int nunits = Rj >> 3;
         // this warp owns units u = warp + NWARP*t (t = 0, 1, ...), processed two at a time; units 0..3 are the
         // diagonal block
-        const int nmy = (nunits - warp + NWARP - 1) / NWARP;
+        const int nmy = (nunits - gw + TW - 1) / TW;
         const int npairs = max(1, (nmy + 1) >> 1);          // every warp runs pair 0 (it holds the barriers)
+        if (CL) cluster_sync_all();                          // panel j-1 (factor rows, wres) visible cluster-wide
         fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
         __syncthreads();
         GGP_TICK(0);
@@ -352,7 +366,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
             int rb[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                rb[i] = row0 + 8 * (warp + NWARP * (t0 + ((i < nu) ? i : 0)));
+                rb[i] = row0 + 8 * (gw + TW * (t0 + ((i < nu) ? i : 0)));
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
             }
@@ -377,7 +391,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                 __syncthreads();          // every warp is done with its covariance scratch (it aliases D)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int u = warp + NWARP * i;
+                    const int u = gw + TW * i;
                     if (i < nu && u < 4) {
 #pragma unroll
                         for (int cb = 0; cb < 4; ++cb)
@@ -387,6 +401,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                     }
                 }
                 GGP_TICK(1);
+                if (!CL || crank == 0) {
                 __syncthreads();                                                 // (A)
                 GGP_TICK(2);
                 if (warp == 0) {
@@ -431,19 +446,20 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                         if (bad) break;
                     }
                     GGP_TICKW(0, 10, D[lane * D_LD + 31]);
-                    if (bad) { if (lane == 0) sm.flag[0] = bad; }
+                    if (bad) { if (lane == 0) { sm.flag[0] = bad; if (CL) aux[Mp + 32] = (double)bad; } }
                     else logdet += 0.5 * log(mypiv);
                 }
                 GGP_TICK(3);
                 __syncthreads();                                                 // (B0)
                 GGP_TICK(4);
-                if (sm.flag[0] != 0) {
+                const bool failed = sm.flag[0] != 0;
+                if (!CL && failed) {
                     if (tid == 0 && info) *info = sm.flag[0];
                     return -INFINITY;
                 }
-                if (warp == 0) {
+                if (warp == 0 && !failed) {
                     // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]
-                    double b = sm.wres[row0 + lane];
+                    double b = wres[row0 + lane];
                     GGP_TICKW(0, 11, b);
                     double myu = 0.0;
 #pragma unroll 1
@@ -453,6 +469,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                         if (lane > c) b = fma(-D[lane * D_LD + c], uc, b);
                     }
                     sm.uj[lane] = myu;
+                    if (CL) aux[Mp + lane] = myu;
                     quad += myu * myu;
                     if (u_out) u_out[row0 + lane] = myu;
                     // store the diagonal rows of L (zeros above the diagonal)
@@ -466,7 +483,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                         }
                     }
                     GGP_TICKW(0, 12, quad);
-                } else if (warp == 1) {
+                } else if (warp == 1 && !failed) {
                     // Minv = Ljj^-1: lane k solves Ljj y = e_k.  Rows in blocks of 8: the contribution of all earlier
                     // rows is accumulated for the 8 rows at once (one own-column load + four broadcast LDS.128 of
                     // LT[t][i0..i0+7] per t), then an 8x8 triangular solve in registers.
@@ -506,12 +523,27 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                 GGP_TICK(5);
                 __syncthreads();                                                 // (B)
                 GGP_TICK(6);
+                }
+                if (CL) {
+                    cluster_sync_all();                      // Minv, u block, diagonal rows and flag published by CTA 0
+                    const int fl = (int)aux[Mp + 32];
+                    if (fl != 0) {
+                        if (crank == 0 && tid == 0 && info) *info = fl;
+                        return -INFINITY;
+                    }
+                    if (crank != 0) {
+                        const double* gm = Lp + minv_off(Mp) + 1024LL * j;
+                        for (int idx = tid; idx < 1024; idx += NT) sm.Minv[(idx >> 5) * MI_LD + (idx & 31)] = __ldcg(gm + idx);
+                        if (tid < 32) sm.uj[tid] = __ldcg(aux + Mp + tid);
+                        __syncthreads();
+                    }
+                }
             }
 
             // ------------------------------------------------------------------ 4. X = P Minv^T, store, update w
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                if (i < nu && !(pr == 0 && warp + NWARP * i < 4)) {
+                if (i < nu && !(pr == 0 && gw + TW * i < 4)) {
                     GGP_TICKW(2, 23, acc[i][0][0]);
                     double xt[4][2];
                     unit_trsm(acc[i], xt, sm.Minv, g, q);
@@ -528,13 +560,13 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                     double sdot = s0 + s1;
                     sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
                     sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-                    if (q == 0) sm.wres[r] -= sdot;
+                    if (q == 0) wres[r] -= sdot;
                     GGP_TICKW(2, 22, sdot);
                 }
             }
         }
         GGP_TICK(7);
-        __syncthreads();                                                         // (C)
+        if (!CL) __syncthreads();                                                // (C)  (cluster variant: barrier at the top)
         GGP_TICK(8);
     }
 
@@ -544,8 +576,38 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         if (lane == 0) sm.red[0] = -ld - 0.5 * qd;
     }
     __syncthreads();
-    if (tid == 0 && info) *info = 0;
+    if (crank == 0 && tid == 0 && info) *info = 0;
     return sm.red[0];
+}
+
+// Cluster size for `ntasks` independent matrices: one CTA per matrix when the machine is already full, otherwise
+// the largest power of two (<= 8, the portable cluster limit) that still fits all clusters in one wave of
+// GGP_CTAS_PER_SM resident CTAs per SM.  GGP_CLUSTER=<n> overrides (developer experiments).
+inline int choose_cluster(long long ntasks)
+{
+    if (const char* e = getenv("GGP_CLUSTER")) {
+        int g = atoi(e);
+        if (g == 1 || g == 2 || g == 4 || g == 8) return g;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long slots = (long long)sms * GGP_CTAS_PER_SM;
+    int g = 1;
+    while (g < 8 && ntasks * (g * 2) <= slots) g *= 2;
+    return g;
+}
+
+template <typename K, typename... Args>
+inline cudaError_t launch_maybe_cluster(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, int G, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = (G > 1) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 }  // namespace ggp

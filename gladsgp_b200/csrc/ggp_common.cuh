@@ -54,9 +54,15 @@ __host__ __device__ inline long long panel_off(int kb, int Mp) {
 }
 // after the panels: nP inverted diagonal blocks, [nP][32][32] row-major (Minv[c][k] = (Ljj^-1)[c][k])
 __host__ __device__ inline long long minv_off(int Mp) { return panel_off(Mp / 32, Mp); }
-__host__ __device__ inline long long packed_doubles(int Mp) {
-    int nP = Mp / 32;
-    return panel_off(nP, Mp) + 1024LL * nP;
+// after those: auxiliary area of the cluster (multi-CTA) variant: running forward solve wres[Mp], the current
+// u block [32], a failure flag [32]
+__host__ __device__ inline long long aux_off(int Mp) { return panel_off(Mp / 32, Mp) + 1024LL * (Mp / 32); }
+__host__ __device__ inline long long packed_doubles(int Mp) { return aux_off(Mp) + Mp + 64; }
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8).  SASS: DMMA.8x8x4

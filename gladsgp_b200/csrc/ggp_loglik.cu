@@ -155,6 +155,7 @@ cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // (2) batched fused log-likelihood: one CTA per matrix.
 // ---------------------------------------------------------------------------------------------
+template <bool CL>
 __global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const double* __restrict__ W,
                       long long w_stride, const double* __restrict__ beta, const double* __restrict__ lamz,
@@ -163,11 +164,11 @@ loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
-    const int b = blockIdx.x;
-    double ll = eval_block_loglik(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
-                                  W + (size_t)b * w_stride, Lws + (size_t)b * l_stride,
-                                  u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
-    if (threadIdx.x == 0) loglik[b] = ll;
+    const int b = CL ? blockIdx.x / cluster_nctarank() : blockIdx.x;
+    double ll = eval_block_loglik<CL>(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
+                                      W + (size_t)b * w_stride, Lws + (size_t)b * l_stride,
+                                      u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
+    if (threadIdx.x == 0 && (!CL || cluster_ctarank() == 0)) loglik[b] = ll;
 }
 
 // packed factor -> dense lower-triangular (m x m row-major), for tests / inspection
@@ -271,13 +272,19 @@ int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long 
         return GGP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
-    // GGP_DEBUG_SHARED_WS=1 (developer experiment): every CTA scribbles over the same workspace, results are
-    // garbage, timing shows the kernel with an L2-resident factor
-    static const bool shared_ws = getenv("GGP_DEBUG_SHARED_WS") != nullptr;
-    loglik_batched_kernel<<<B, NT, smem, st>>>(X, m, Mp, d, W, w_stride, beta, lamz, diag_add, factor_ws,
-                                               shared_ws ? 0 : packed_doubles(Mp), u_out, loglik_out, info_out);
+    const int G = choose_cluster(B);
+    const long long ls = packed_doubles(Mp);
+    if (G > 1) {
+        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
+        GGP_CUDA(launch_maybe_cluster(loglik_batched_kernel<true>, dim3(B * G), dim3(NT), smem, st, G, X, m, Mp, d, W, w_stride,
+                                      beta, lamz, diag_add, factor_ws, ls, u_out, loglik_out, info_out));
+    } else {
+        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
+        loglik_batched_kernel<false><<<B, NT, smem, st>>>(X, m, Mp, d, W, w_stride, beta, lamz, diag_add, factor_ws, ls, u_out,
+                                                          loglik_out, info_out);
+    }
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }

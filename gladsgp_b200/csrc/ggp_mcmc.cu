@@ -114,6 +114,7 @@ __device__ inline void gather_block_params(const ggp_mcmc_args& a, const double*
     diag_add = 1.0 / (a.lamsim[j] * lamwos) + 1.0 / lamws;
 }
 
+template <bool CL>
 __global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, int t)
 {
@@ -121,7 +122,8 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
     const int Mp = round_up32(a.m);
     EvalSmem sm = carve_eval_smem(smem_raw, Mp, a.d);
     __shared__ double beta_sm[64];
-    const int j = blockIdx.x, c = blockIdx.y;
+    const int j = CL ? blockIdx.x / cluster_nctarank() : blockIdx.x, c = blockIdx.y;
+    const bool lead = (threadIdx.x == 0) && (!CL || cluster_ctarank() == 0);    // the one thread that owns the state
     const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
     double* th = a.theta + (size_t)c * P;
     double* sig = a.sigwl + (size_t)c * pu;
@@ -134,7 +136,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
         const size_t o = (size_t)c * P + s;
         const int valid = pl.valid[o];
         if (!valid) {
-            if (threadIdx.x == 0 && accd) accd[s] = 0;
+            if (lead && accd) accd[s] = 0;
             continue;
         }
         const double cand = pl.cand[o];
@@ -142,8 +144,8 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
         __syncthreads();
         gather_block_params(a, th, j, s, cand, beta_sm, lamz, diag_add);
         __syncthreads();
-        const double ll_new = eval_block_loglik(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, nullptr, nullptr);
-        if (threadIdx.x == 0) {
+        const double ll_new = eval_block_loglik<CL>(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, nullptr, nullptr);
+        if (lead) {
             if (a.eval_count) atomicAdd(a.eval_count, 1ULL);
             const double ll_old = sig[j];
             const double xold = th[s];
@@ -156,11 +158,13 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
             }
             if (accd) accd[s] = acc ? 1 : 0;
         }
-        __syncthreads();
+        if (CL) cluster_sync_all();        // the accepted state is visible to every CTA of the cluster
+        else __syncthreads();
     }
 }
 
 // mode 0: sigwl <- per-PC terms of the current state.  mode 1: sigwl_cand <- terms under candidate lamWOs.
+template <bool CL>
 __global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride,
                 double* __restrict__ sig_cand, int mode)
@@ -169,7 +173,7 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
     const int Mp = round_up32(a.m);
     EvalSmem sm = carve_eval_smem(smem_raw, Mp, a.d);
     __shared__ double beta_sm[64];
-    const int j = blockIdx.x, c = blockIdx.y;
+    const int j = CL ? blockIdx.x / cluster_nctarank() : blockIdx.x, c = blockIdx.y;
     const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
     const double* th = a.theta + (size_t)c * P;
     double* Lp = Lws + ((size_t)c * pu + j) * l_stride;
@@ -184,9 +188,9 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
     double lamz, diag_add;
     gather_block_params(a, th, j, site, cand, beta_sm, lamz, diag_add);
     __syncthreads();
-    const double ll = eval_block_loglik(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, a.W + (size_t)j * a.m, Lp,
-                                        nullptr, nullptr);
-    if (threadIdx.x == 0) {
+    const double ll = eval_block_loglik<CL>(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, a.W + (size_t)j * a.m, Lp,
+                                            nullptr, nullptr);
+    if (threadIdx.x == 0 && (!CL || cluster_ctarank() == 0)) {
         if (mode == 0) a.sigwl[(size_t)c * pu + j] = ll;
         else sig_cand[(size_t)c * pu + j] = ll;
         if (a.eval_count) atomicAdd(a.eval_count + 1, 1ULL);
@@ -287,10 +291,19 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         return GGP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    GGP_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GGP_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
-    GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
+    const int G = choose_cluster((long long)a.pu * a.n_chains);
+    const int cpct = eval_carveout_pct(smem);
+    if (G > 1) {
+        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+    } else {
+        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+    }
 
     const size_t P = (size_t)a.d * a.pu + 2 * a.pu + 1;
     unsigned char* p = reinterpret_cast<unsigned char*>(a.workspace);
@@ -303,11 +316,21 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     pl.valid = reinterpret_cast<int*>(p);     p += align256((size_t)a.n_chains * P * sizeof(int));
     double* sig_cand = reinterpret_cast<double*>(p);
     const long long l_stride = packed_doubles(Mp);
-    const dim3 grid(a.pu, a.n_chains);
+    const dim3 grid(a.pu * G, a.n_chains);
     const int cb = (a.n_chains + 31) / 32;
 
+    auto launch_eval_all = [&](int mode) -> cudaError_t {
+        if (G > 1) return launch_maybe_cluster(eval_all_kernel<true>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode);
+        eval_all_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
+        return cudaSuccess;
+    };
+    auto launch_sweep = [&](int t) -> cudaError_t {
+        if (G > 1) return launch_maybe_cluster(sweep_kernel<true>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, t);
+        sweep_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
+        return cudaSuccess;
+    };
     if (a.init_sigwl) {
-        eval_all_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, 0);
+        GGP_CUDA(launch_eval_all(0));
         GGP_CUDA(cudaGetLastError());
     }
     // optional per-kernel device timing (CUDA events on the launching stream)
@@ -320,9 +343,9 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     for (int t = 0; t < a.n_steps; ++t) {
         plan_kernel<<<cb, 32, 0, st>>>(a, pl, t);
         if (timed) cudaEventRecord(ev[3 * t + 0], st);
-        sweep_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
+        launch_sweep(t);
         if (timed) cudaEventRecord(ev[3 * t + 1], st);
-        eval_all_kernel<<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, 1);
+        launch_eval_all(1);
         if (timed) cudaEventRecord(ev[3 * t + 2], st);
         finalize_kernel<<<cb, 32, 0, st>>>(a, pl, sig_cand, t);
     }
