@@ -169,3 +169,26 @@ def test_loglik_large_m_many_inputs(cuda):
         u = scipy.linalg.solve_triangular(L, W[b], lower=True)
         ref = -np.sum(np.log(np.diag(L))) - 0.5 * u @ u
         assert abs(ll[b] - ref) <= LL_RTOL * abs(ref)
+
+
+def test_cluster_and_single_cta_variants_agree_bitwise(cuda, monkeypatch):
+    """Small batches run one matrix per thread-block cluster (up to 8 CTAs); the per-unit arithmetic is the same
+    as in the one-CTA-per-matrix variant, so results must be bit-identical."""
+    from gladsgp_b200 import ops
+    pr = make_problem(m=257, q=4, pu=2)
+    num = pr['num']
+    beta, lamz, lamws, lamwos = random_hypers(num, 2, seed=5)
+    dadd = 1.0 / (num.LamSim * lamwos) + 1.0 / lamws
+    W = num.w.T.copy()
+    res = {}
+    for g in ('1', '2', '8'):
+        monkeypatch.setenv('GGP_CLUSTER', g)
+        out = ops.loglik_batched(num.zt, W, beta, lamz, dadd, want_factor=True, want_u=True)
+        res[g] = (out['loglik'].cpu().numpy(), ops.factor_unpack(out['factor'], 257).cpu().numpy(), out['u'].cpu().numpy())
+    for g in ('2', '8'):
+        for a, b in zip(res['1'], res[g]):
+            assert np.array_equal(a, b)
+    # failure is reported consistently by every CTA of the cluster
+    monkeypatch.setenv('GGP_CLUSTER', '8')
+    bad = ops.loglik_batched(num.zt, W, np.full((2, num.d), 1e-6), np.ones(2), np.full(2, -0.999999))
+    assert np.all(bad['loglik'].cpu().numpy() == -np.inf) and np.all(bad['info'].cpu().numpy() > 0)

@@ -10,7 +10,8 @@ rng=np.random.default_rng(0)
 B=2
 beta=np.exp(rng.uniform(np.log(0.05),np.log(1.0),size=(B,q+1))); lamz=np.array([0.9,1.4]); dadd=np.array([2e-3,5e-3])
 W=rng.standard_normal((B,m))
-t0=time.time(); out=ops.loglik_batched(X,W,beta,lamz,dadd); ll=out['loglik'].cpu().numpy(); print('gpu',time.time()-t0, ll, out['info'].cpu().numpy())
+out=ops.loglik_batched(X,W,beta,lamz,dadd); torch.cuda.synchronize()
+t0=time.time(); out=ops.loglik_batched(X,W,beta,lamz,dadd); ll=out['loglik'].cpu().numpy(); print('gpu seconds (2 matrices, warm)',time.time()-t0, ll, out['info'].cpu().numpy())
 import scipy.linalg
 for b in range(B):
     D=((X[:,None,:]-X[None,:,:])**2)@beta[b]
