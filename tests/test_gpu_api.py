@@ -216,3 +216,20 @@ def test_batched_chains_equal_independent_single_chains(cuda):
     np.random.seed(1)
     d2, l2 = model.do_mcmc_chains(4, 2)
     assert d2.shape == (4, 2, P) and l2.shape == (4, 2) and np.all(np.isfinite(l2))
+
+
+def test_reference_workflow_end_to_end(cuda, tmp_path):
+    """fit_models -> load_model -> batched prediction, reduced cfg 1 shape (examples/synthetic_fit_predict.py)."""
+    import subprocess, sys
+    from helpers import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'examples', 'synthetic_fit_predict.py'), str(tmp_path),
+                          '--m', '64', '--nx', '60', '--nt', '12', '--mcmc', '96', '--tune', '20', '--ntest', '8'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    files = os.listdir(os.path.join(tmp_path, 'data', 'models'))
+    for f in ('pca_synthetic_n064_U.npy', 'pca_synthetic_n064_S.npy', 'pca_synthetic_n064_Vh.npy',
+              'synthetic_n064_p05.pkl', 'timing.csv'):
+        assert f in files, files
+    line = [l for l in out.stdout.splitlines() if l.startswith('test RMSE')][0]
+    rmse = float(line.split()[2]); cover = float(line.split()[-1])
+    assert rmse < 0.2 and 0.6 < cover <= 1.0, line
