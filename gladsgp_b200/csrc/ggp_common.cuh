@@ -37,11 +37,8 @@ constexpr int NWARP = NT / 32;
 #ifndef GGP_CTAS_PER_SM
 #define GGP_CTAS_PER_SM 4     // 4 warps x 4 CTAs per SM, 128 registers per thread (tools/quick_bench.py sweep)
 #endif
-constexpr int PASS_UNITS = 4 * NWARP;      // 8-row units per pass (4 per warp: 64 accumulator registers)
-constexpr int PASS_ROWS = 8 * PASS_UNITS;  // rows handled per pass
 constexpr int D_LD = 33;        // staging of the 32x32 diagonal block
 constexpr int MI_LD = 40;       // leading dimension of the inverted diagonal block (conflict-free LDS.128)
-constexpr int PS_LD = 33;       // leading dimension of the panel staging buffer (odd: conflict-free rows)
 constexpr int LT_LD = 34;       // leading dimension of the transposed diagonal factor (even: 16 B pairs)
 
 __host__ __device__ inline int round_up32(int m) { return (m + 31) & ~31; }

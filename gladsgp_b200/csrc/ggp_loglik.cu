@@ -8,9 +8,10 @@ namespace ggp {
 
 // ---------------------------------------------------------------------------------------------
 // (1) product squared-exponential covariance, materialised (SepiaDistCov type 1).
-// HBM-write bound: 8*m*m bytes per matrix.  One CTA per (64x64 tile pair, matrix): the tile
-// (bi >= bj) is computed once (half the exps) and written twice -- directly and transposed
-// through shared memory, both as coalesced 16-byte stores.
+// 8*m*m bytes written per matrix.  One CTA per (64x64 tile pair, matrix): the tile (bi >= bj) is
+// computed once (half the exps; 4x4 distances per thread in registers, in-kernel exp) and written
+// twice -- directly and transposed through shared memory, both as 16-byte streaming stores.
+// Measured 2.8 TB/s: the double-precision exponential, not HBM, is the bound (profiles/r1_cov_build_summary.txt).
 // ---------------------------------------------------------------------------------------------
 constexpr int CT = 64;
 
