@@ -32,7 +32,7 @@ class McmcArgs(C.Structure):
     ]
 
 
-_I, _LL, _P, _D = C.c_int, C.c_longlong, C.c_void_p, C.c_double
+_I, _LL, _P, _D, _F = C.c_int, C.c_longlong, C.c_void_p, C.c_double, C.c_float
 
 # name -> (restype, argtypes); mirrors include/gladsgp_b200.h one to one
 SIGNATURES = {
@@ -57,6 +57,10 @@ SIGNATURES = {
     'ggp_rsvd_workspace_bytes': (_LL, [_I]),
     'ggp_rsvd_sketch_f32': (_I, [_P, _I, _LL, _P, _I, _P, _P, _LL, _P]),
     'ggp_rsvd_xty_f32': (_I, [_P, _I, _LL, _P, _I, _P, _P]),
+    'ggp_colstats_f32': (_I, [_P, _LL, _I, _LL, _I, _I, _F, _P, _P, _P]),
+    'ggp_standardize_f32': (_I, [_P, _LL, _I, _LL, _I, _P, _LL, _P, _LL, _P, _P]),
+    'ggp_project_workspace_bytes': (_LL, [_I, _I]),
+    'ggp_project_f32': (_I, [_P, _I, _LL, _P, _I, _P, _P, _LL, _P]),
 }
 
 

@@ -11,24 +11,34 @@ from sepia.SepiaModel import SepiaModel
 from sepia.SepiaData import SepiaData
 from sepia import SepiaParam
 
-from . import svd
+from . import svd, ingest
 
 PMAX = 25      # src/model.py:81
 
 
 def init_model(t_std, y_sim, exp, p, data_dir='data/', sd_threshold=1e-6, recompute=False):
+    """src/model.py:20-107.  y_sim may be the transposed view of the (n_y, m) ensemble file (np.load(path).T[:m],
+    no host copy): large float32 ensembles are uploaded once as stored and every pass over them (column statistics,
+    standardisation, rSVD, projection) runs on the device."""
     y_ind_sim = np.linspace(0, 1, y_sim.shape[1])
     data = SepiaData(t_sim=t_std, y_sim=y_sim, y_ind_sim=y_ind_sim)
-    mu_y = np.mean(y_sim, axis=0)
-    sd_y = np.std(y_sim, ddof=1, axis=0)
-    sd_y[sd_y < sd_threshold] = sd_threshold
+    on_device = ingest.use_device(y_sim.size) and y_sim.dtype == np.float32
+    if on_device:
+        ydev, tr = data.sim_data.y_device()
+        mu_d, sd_d = ingest.column_stats(ydev, transposed=tr, sd_threshold=sd_threshold)      # src/model.py:60-64
+        mu_y, sd_y = mu_d.cpu().numpy(), sd_d.cpu().numpy()
+    else:
+        mu_y = np.mean(y_sim, axis=0)
+        sd_y = np.std(y_sim, ddof=1, axis=0)
+        sd_y[sd_y < sd_threshold] = sd_threshold
     data.transform_xt(t_notrans=np.arange(t_std.shape[1]))
     data.standardize_y(y_mean=mu_y, y_sd=sd_y)
     os.makedirs(data_dir, exist_ok=True)
     pat = os.path.join(data_dir, 'pca_{}_{}.npy')
     have = all(os.path.exists(pat.format(exp, a)) for a in ('U', 'S', 'Vh'))
     if recompute or not have:
-        U, S, Vh = svd.randomized_svd(data.sim_data.y_std, PMAX, k=0, q=1)
+        U, S, Vh = svd.randomized_svd(data.sim_data.y_std_device() if on_device else data.sim_data.y_std,
+                                      PMAX, k=0, q=1)
         np.save(pat.format(exp, 'U'), U[:, :PMAX])
         np.save(pat.format(exp, 'S'), S)
         np.save(pat.format(exp, 'Vh'), Vh[:PMAX, :])
@@ -43,7 +53,14 @@ def init_model(t_std, y_sim, exp, p, data_dir='data/', sd_threshold=1e-6, recomp
 
 
 def pc_precision(sim_data):
-    """src/model.py:219-223: 1 / var(y_std - w K), streamed over column blocks."""
+    """src/model.py:219-223: 1 / var(y_std - w K).  Large ensembles: from the device projection pass (shared with
+    SepiaModel.__init__); small ones: streamed over column blocks on the host."""
+    if getattr(sim_data, '_proj', None) is not None:
+        return ingest.pc_precision_from(sim_data._proj)
+    if (ingest.use_device(sim_data.y.size) and np.asarray(sim_data.K).dtype == np.float32 and
+            (sim_data._y_std_dev is not None or sim_data._y_std.dtype == np.float32)):
+        sim_data._proj = ingest.project_basis(sim_data.y_std_device(), sim_data.K_device())
+        return ingest.pc_precision_from(sim_data._proj)
     K = np.asarray(sim_data.K, dtype=np.float64)
     G = K @ K.T
     n = 0
@@ -68,9 +85,16 @@ def override_lamWOs(model, pc_prec, gamma_a=50):
     model.params.mcmcList = [model.params.betaU, model.params.lamUz, model.params.lamWs, model.params.lamWOs]
 
 
+def _load_ensemble(path, dtype):
+    """np.load(path).T.astype(dtype) (src/model.py:133,185) without the host transpose when the file already has the
+    requested dtype: the (m, n_y) result is then a view of the (n_y, m) file array and is transposed on the device."""
+    a = np.load(path)
+    return a.T if a.dtype == dtype else a.T.astype(dtype)
+
+
 def load_model(train_config, m, p, dtype=np.float32):
     t_std = np.loadtxt(train_config.X_standard, delimiter=',', skiprows=1, comments=None).astype(dtype)[:m]
-    y_sim = np.load(train_config.Y_physical).T.astype(dtype)[:m]
+    y_sim = _load_ensemble(train_config.Y_physical, dtype)[:m]
     data_dir = os.path.join(train_config.data_dir, 'models')
     os.makedirs(data_dir, exist_ok=True)
     model_path = os.path.join(data_dir, '{}_n{:03d}_p{:02d}'.format(train_config.exp, m, p))
@@ -83,7 +107,7 @@ def load_model(train_config, m, p, dtype=np.float32):
 
 def fit_models(train_config, n_sims, n_pcs, dtype=np.float32, recompute=False, n_tune=(100, 5), n_mcmc=512):
     t_std = np.loadtxt(train_config.X_standard, delimiter=',', skiprows=1, comments=None).astype(dtype)
-    y_sim = np.load(train_config.Y_physical).T.astype(dtype)
+    y_sim = _load_ensemble(train_config.Y_physical, dtype)
     data_dir = os.path.join(train_config.data_dir, 'models')
     os.makedirs(data_dir, exist_ok=True)
     models, rows = [], []

@@ -308,3 +308,54 @@ def rsvd_xty(X, Y):
     Bt = torch.empty((r, n), dtype=torch.float32, device='cuda')
     check(lib.ggp_rsvd_xty_f32(ptr(X), m, n, ptr(Y.contiguous()), r, ptr(Bt), stream_ptr()), 'ggp_rsvd_xty_f32')
     return Bt
+
+
+# ------------------------------------------------------------------ ensemble ingest
+def _ens_dims(Y, transposed):
+    if Y.dim() != 2 or Y.stride(1) != 1 or Y.dtype != _lib.require_cuda().float32:
+        raise ValueError('ensemble must be a 2-D float32 device tensor with unit column stride')
+    m, n = (Y.shape[1], Y.shape[0]) if transposed else Y.shape
+    return m, n, Y.stride(0)
+
+
+def colstats(Y, transposed=False, ddof=1, sd_floor=0.0):
+    """Column mean and standard deviation of the ensemble (src/model.py:60-64).  Y: device float32 (m, n), or (n, m)
+    with transposed=True (the file layout); a row-sliced view (y[:m] / yt[:, :m]) is used in place.
+    Returns (mean, sd), float32 device vectors of length n."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    m, n, ld = _ens_dims(Y, transposed)
+    mean = torch.empty(n, dtype=torch.float32, device='cuda')
+    sd = torch.empty(n, dtype=torch.float32, device='cuda')
+    check(lib.ggp_colstats_f32(ptr(Y), ld, m, n, int(bool(transposed)), int(ddof), float(sd_floor), ptr(mean), ptr(sd),
+                               stream_ptr()), 'ggp_colstats_f32')
+    return mean, sd
+
+
+def standardize(Y, mean, sd, transposed=False, out=None):
+    """(Y - mean) / sd in float32 -> (m, n) device tensor (SepiaData.standardize_y; src/model.py:71-72)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    m, n, ld = _ens_dims(Y, transposed)
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device='cuda')
+    check(lib.ggp_standardize_f32(ptr(Y), ld, m, n, int(bool(transposed)), ptr(mean), mean.numel(), ptr(sd), sd.numel(),
+                                  ptr(out), stream_ptr()), 'ggp_standardize_f32')
+    return out
+
+
+def project(X, Kt):
+    """P (m, pu+2) float64 = [X @ Kt.T, X.sum(1), (X*X).sum(1)] accumulated in FP64 (src/model.py:219-223)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    m, n = X.shape
+    pu = Kt.shape[0]
+    if Kt.shape[1] != n:
+        raise ValueError('Kt must be (pu, n)')
+    nb = lib.ggp_project_workspace_bytes(m, pu)
+    if nb < 0:
+        raise ValueError('project: pu must be in [1, 32]')
+    ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
+    P = torch.empty((m, pu + 2), dtype=torch.float64, device='cuda')
+    check(lib.ggp_project_f32(ptr(X), m, n, ptr(Kt), pu, ptr(P), ptr(ws), ws.numel(), stream_ptr()), 'ggp_project_f32')
+    return P

@@ -2,12 +2,19 @@
 
 Call sites: /root/reference/src/model.py:57,68,71,102;
 experiments/synthetic/analysis/fit_scalar_models.py:45-47; sensitivity_indices.py:183.
-Pure host-side container logic (no heavy arithmetic): input scaling, y standardisation, K basis.
+Host-side container logic (input scaling, K basis).  Large ensembles (>= ingest.DEVICE_MIN_ELEMS elements) are
+standardised on the GPU (csrc/ggp_ingest.cu) and kept device-resident for the rSVD and projection passes; the host
+copy of `y_std` is then only materialised when a caller reads it.
 """
 import numpy as np
 
+from .. import ingest
+
 
 class DataContainer:
+    """sim_data: x, t, y, y_ind, x_trans, t_trans, y_std, K, orig_y_mean / orig_y_sd (SEPIA's DataContainer).
+    y_std and K carry an optional device copy (torch CUDA tensor) next to the host array."""
+
     def __init__(self, x, y, t=None, y_ind=None):
         self.x = x
         self.y = y
@@ -15,12 +22,80 @@ class DataContainer:
         self.y_ind = y_ind
         self.x_trans = None
         self.t_trans = None
-        self.y_std = None
-        self.K = None
+        self._y_std = None
+        self._y_std_dev = None
+        self._y_dev = None            # (tensor, transposed) raw ensemble, dropped once standardised
+        self._K = None
+        self._K_dev = None
+        self._stat_dev = None         # (sd, mean) device copies for get_y
+        self._proj = None             # cached projection on K (w, K K^T, residual sums)
         self.orig_y_mean = None
         self.orig_y_sd = None
         self.orig_x_min = self.orig_x_max = None
         self.orig_t_min = self.orig_t_max = None
+
+    # -- y_std: host array, downloaded from the device copy on first read
+    @property
+    def y_std(self):
+        if self._y_std is None and self._y_std_dev is not None:
+            self._y_std = self._y_std_dev.cpu().numpy()
+        return self._y_std
+
+    @y_std.setter
+    def y_std(self, v):
+        self._y_std = v
+        self._y_std_dev = None
+        self._proj = None
+
+    def has_y_std(self):
+        return self._y_std is not None or self._y_std_dev is not None
+
+    def y_std_device(self):
+        if self._y_std_dev is None:
+            self._y_std_dev = ingest.upload(self._y_std)
+        return self._y_std_dev
+
+    def y_device(self):
+        """Raw ensemble on the device as (tensor, transposed).  An (n_y, m)-major array viewed through `.T` (the
+        reference's np.load(Y_physical).T, src/model.py:133) is uploaded as stored and transposed on the device."""
+        if self._y_dev is None:
+            y = self.y
+            if y.dtype == np.float32 and not y.flags['C_CONTIGUOUS'] and y.T.strides[1] == y.itemsize:
+                self._y_dev = (ingest.upload(np.ascontiguousarray(y.T)), True)
+            else:
+                self._y_dev = (ingest.upload(y), False)
+        return self._y_dev
+
+    @property
+    def K(self):
+        return self._K
+
+    @K.setter
+    def K(self, v):
+        self._K = v
+        self._K_dev = None
+        self._proj = None
+
+    def K_device(self):
+        if self._K_dev is None:
+            self._K_dev = ingest.upload(self._K)
+        return self._K_dev
+
+    def stats_device(self):
+        """(orig_y_sd, orig_y_mean) as flat float32 device vectors (length 1 or n_y)."""
+        key = (id(self.orig_y_sd), id(self.orig_y_mean))
+        if self._stat_dev is None or self._stat_dev[0] != key:
+            self._stat_dev = (key, ingest.upload(np.asarray(self.orig_y_sd, dtype=np.float32).reshape(-1)),
+                              ingest.upload(np.asarray(self.orig_y_mean, dtype=np.float32).reshape(-1)))
+        return self._stat_dev[1], self._stat_dev[2]
+
+    def __getstate__(self):           # device tensors do not travel in pickles
+        st = dict(self.__dict__)
+        if st.get('_y_std') is None and st.get('_y_std_dev') is not None:
+            st['_y_std'] = st['_y_std_dev'].cpu().numpy()
+        for k in ('_y_std_dev', '_y_dev', '_K_dev', '_stat_dev'):
+            st[k] = None
+        return st
 
 
 class SepiaData:
@@ -117,6 +192,8 @@ class SepiaData:
     def standardize_y(self, center=True, scale='scalar', y_mean=None, y_sd=None):
         sd = self.sim_data
         y = sd.y
+        if ingest.use_device(y.size) and y.dtype == np.float32:
+            return self._standardize_y_device(center, scale, y_mean, y_sd)
         if y_mean is None:
             y_mean = np.mean(y, axis=0) if center else 0.0
         if y_sd is None:
@@ -131,7 +208,45 @@ class SepiaData:
                 raise ValueError('scale must be "scalar", "columnwise" or False')
         sd.orig_y_mean = y_mean
         sd.orig_y_sd = y_sd
+        sd._stat_dev = None
         sd.y_std = (y - y_mean) / y_sd
+
+    def _standardize_y_device(self, center, scale, y_mean, y_sd):
+        """Same rules on the GPU (ggp_colstats_f32 / ggp_standardize_f32); y_std stays on the device."""
+        from .. import ops
+        sd = self.sim_data
+        m, n = sd.y.shape
+        ydev, tr = sd.y_device()
+        if scale not in ('scalar', 'columnwise', False):
+            raise ValueError('scale must be "scalar", "columnwise" or False')
+        if y_mean is None or y_sd is None:
+            cm, cs = ops.colstats(ydev, transposed=tr, ddof=1, sd_floor=0.0)
+            if y_mean is None:
+                y_mean = cm.cpu().numpy() if center else 0.0
+            if y_sd is None:
+                if scale == 'columnwise':
+                    y_sd = cs.cpu().numpy()
+                elif scale is False:
+                    y_sd = 1.0
+                else:
+                    # np.std(y - y_mean, ddof=1) over all elements, from the column sums
+                    cmh = cm.double().cpu().numpy()
+                    ss = float(np.sum(cs.double().cpu().numpy() ** 2) * (m - 1))
+                    if np.ndim(y_mean) == 0 or not center:
+                        resid_mean = cmh - np.asarray(y_mean, dtype=np.float64)
+                        ss += m * float(np.sum((resid_mean - resid_mean.mean()) ** 2))
+                    y_sd = np.float32(np.sqrt(ss / (m * n - 1)))
+        mean_h = np.asarray(y_mean, dtype=np.float32).reshape(-1)
+        sd_h = np.asarray(y_sd, dtype=np.float32).reshape(-1)
+        if mean_h.size not in (1, n) or sd_h.size not in (1, n):
+            raise ValueError('y_mean / y_sd must be scalars or have one entry per column of y_sim')
+        sd.orig_y_mean = y_mean
+        sd.orig_y_sd = y_sd
+        sd._stat_dev = ((id(y_sd), id(y_mean)), ingest.upload(sd_h), ingest.upload(mean_h))
+        sd._y_std = None
+        sd._proj = None
+        sd._y_std_dev = ops.standardize(ydev, sd._stat_dev[2], sd._stat_dev[1], transposed=tr)
+        sd._y_dev = None              # the raw device copy is not needed again
 
     def create_K_basis(self, n_pc=0.995, K=None):
         if self.scalar_out:
@@ -145,7 +260,7 @@ class SepiaData:
                 raise ValueError('K must have shape (pu, %d), got %s' % (sd.y.shape[1], K.shape))
             sd.K = K
             return
-        if sd.y_std is None:
+        if not sd.has_y_std():
             self.standardize_y()
         # SEPIA default: SVD of y_std^T scaled U*s/sqrt(m) (the scaling src/model.py:100-101 refers to)
         m = sd.y_std.shape[0]

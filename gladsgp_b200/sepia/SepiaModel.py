@@ -16,7 +16,7 @@ import sys
 import numpy as np
 
 from .SepiaParam import SepiaParam
-from .. import ops
+from .. import ops, ingest
 from ..ops import PRIOR_KIND, PROP_KIND
 
 
@@ -46,7 +46,7 @@ class SepiaModel:
         sd = data.sim_data
         if sd.x_trans is None or (sd.t is not None and sd.t_trans is None):
             data.transform_xt()
-        if sd.y_std is None:
+        if not sd.has_y_std():
             data.standardize_y()
         if not data.scalar_out and sd.K is None:
             raise ValueError('create_K_basis must be called before SepiaModel for multivariate output')
@@ -76,6 +76,16 @@ class SepiaModel:
             K = np.asarray(sd.K)
             num.pu = K.shape[0]
             n_y = K.shape[1]
+        on_device = (not data.scalar_out and ingest.use_device(m * n_y) and K.dtype == np.float32 and
+                     (sd._y_std_dev is not None or sd._y_std.dtype == np.float32))
+        if on_device:
+            # large ensemble: one streaming pass on the device (csrc/ggp_ingest.cu), FP64 accumulation
+            if sd._proj is None:
+                sd._proj = ingest.project_basis(sd.y_std_device(), sd.K_device())
+            w = sd._proj['w']
+            num.LamSim = np.diag(sd._proj['G']).copy()
+            resid_ss = sd._proj['resid_ss']
+        elif not data.scalar_out:
             # w = (pinv(K)^T y_std^T)^T  (src/model.py:219 restates it); K K^T is pu x pu
             K64 = K.astype(np.float64)
             G = K64 @ K64.T

@@ -157,7 +157,8 @@ class SepiaEmulatorPrediction(SepiaPrediction):
                 + torch.as_tensor(np.asarray(ymu), device='cuda').to(dt)
             y = y.reshape(ns, npred, -1)
         elif w.dtype == np.float32:
-            y = ops.reconstruct(w.reshape(ns * npred, pu), sd.K, ysd, ymu).reshape(ns, npred, -1)
+            Kd, (sdd, mud) = self._basis_device(), ((1.0, 0.0) if std else sd.stats_device())
+            y = ops.reconstruct(w.reshape(ns * npred, pu), Kd, sdd, mud).reshape(ns, npred, -1)
         else:
             Kd = torch.as_tensor(np.asarray(sd.K), device='cuda').double()
             y = torch.as_tensor(w, device='cuda').double().reshape(ns * npred, pu) @ Kd
@@ -166,6 +167,10 @@ class SepiaEmulatorPrediction(SepiaPrediction):
             y = y.reshape(ns, npred, -1)
         return y if device else y.cpu().numpy()
 
+    def _basis_device(self):
+        """K on the device (cached in sim_data when it is float32: 58 MB at cfg3, re-used by every get_y call)."""
+        sd = self.model.data.sim_data
+        return sd.K_device() if np.asarray(sd.K).dtype == np.float32 else sd.K
 
     def get_y_stats(self, quantile=0.025, noise=None, device=False):
         """Extension: mean over samples of get_y() and the (quantile, 1-quantile) quantiles of
@@ -175,7 +180,8 @@ class SepiaEmulatorPrediction(SepiaPrediction):
         sd = self.model.data.sim_data
         if self.model.data.scalar_out:
             raise NotImplementedError('get_y_stats is for multivariate (K basis) models')
-        m_, lo, hi = ops.reconstruct_stats(np.asarray(self.w, dtype=np.float32), sd.K, sd.orig_y_sd, sd.orig_y_mean,
+        sdd, mud = sd.stats_device()
+        m_, lo, hi = ops.reconstruct_stats(np.asarray(self.w, dtype=np.float32), self._basis_device(), sdd, mud,
                                            q=quantile, noise=noise)
         if device:
             return dict(mean=m_, lq=lo, uq=hi)

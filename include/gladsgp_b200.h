@@ -164,6 +164,27 @@ int ggp_rsvd_sketch_f32(const float* X, int m, long long n, const float* OmegaT,
                         void* workspace, long long workspace_bytes, void* stream);
 int ggp_rsvd_xty_f32(const float* X, int m, long long n, const float* Y, int r, float* Bt_out, void* stream);
 
+/* ---- (5) ensemble ingest and initialisation passes ------------------------------
+ * The streaming work of init_model / fit_models around the PCA, on the (m x n) float32 ensemble:
+ *   src/model.py:60-64    mu = mean(y, 0); sd = std(y, ddof=1, 0); sd[sd < thr] = thr   -> ggp_colstats_f32
+ *   src/model.py:71-72    y_std = (y - mu) / sd          (SepiaData.standardize_y)       -> ggp_standardize_f32
+ *   src/model.py:219-223  w = (pinv(K)^T y_std^T)^T; var(y_std - w K); SepiaModel.__init__ (w, LamSim, lamWOs prior)
+ *                                                                                         -> ggp_project_f32
+ * transposed != 0: the input is stored [n][m] (the ensemble file layout of src/aggregate_outputs.py:61-68, which
+ * the reference transposes on the host, src/model.py:133); outputs are always [m][n].  ld: row stride of the input in
+ * elements (0 = dense), so that the first m simulations of a larger ensemble can be used in place (y_sim[:m]).
+ * mean_len / sd_len: 1 (SEPIA's default scalar standardisation) or n.  sd < sd_floor is replaced by sd_floor.
+ * ggp_project_f32: P_out[m][pu+2] (double) = { X Kt^T (pu columns), row sums of X, row sums of X^2 }, accumulated in
+ * FP64 in a fixed order (deterministic).  With X = y_std it yields w = (y_std K^T)(K K^T)^-1, ||y_std - w K||^2 and
+ * sum(y_std - w K) without a second pass; with X = K it yields K K^T.  pu <= 32. */
+int ggp_colstats_f32(const float* Y, long long ld, int m, long long n, int transposed, int ddof, float sd_floor,
+                     float* mean_out, float* sd_out, void* stream);
+int ggp_standardize_f32(const float* Y, long long ld, int m, long long n, int transposed, const float* mean,
+                        long long mean_len, const float* sd, long long sd_len, float* Ystd_out, void* stream);
+long long ggp_project_workspace_bytes(int m, int pu);
+int ggp_project_f32(const float* X, int m, long long n, const float* Kt, int pu, double* P_out, void* workspace,
+                    long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
