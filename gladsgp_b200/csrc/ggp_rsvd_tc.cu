@@ -1,0 +1,327 @@
+// Randomized-SVD passes on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+// Same products as ggp_rsvd.cu (/root/reference/src/svd.py:52-60) -- Y = X Omega and Bt = Y^T X over the (m x n)
+// float32 ensemble -- but the multiply-adds run as 3xTF32 split products on the tensor pipe, so that the pass is
+// bound by the HBM read of X instead of the FP32 FMA rate:
+//     x = x_hi + x_lo (x_hi = tf32(x), x_lo = tf32(x - x_hi)),   x*o ~= x_hi*o_hi + x_hi*o_lo + x_lo*o_hi
+// (error ~2^-21 relative per product, i.e. FP32-level; the dropped x_lo*o_lo term is 2^-22 smaller than the product).
+// The tensor core adds into its FP32 accumulator with truncation, so a K-chunk (32 columns, 12 accumulator updates)
+// is summed in TMEM and then added to round-to-nearest FP32 register accumulators by the CUDA cores -- the long sum
+// over n never runs inside the tensor core.
+//
+// Operands are staged by the producer warps: global -> registers (split hi/lo) -> shared memory in the UMMA
+// canonical K-major no-swizzle layout (core matrix = 8 rows x 16 bytes; TMA cannot be used because the row pitch of
+// the reference's ensembles, 4*n_y bytes with n_y = 3693*365, is not a multiple of 16 bytes).  One elected thread of
+// the MMA warp issues tcgen05.mma and signals completion with tcgen05.commit on an mbarrier.
+#include "ggp_common.cuh"
+#include "../../include/gladsgp_b200.h"
+
+namespace ggp {
+
+constexpr int TC_ROWS = 256;                 // rows of X per CTA (two M = 128 tiles)
+constexpr int TC_K = 32;                     // columns of X per chunk (four K = 8 steps)
+constexpr int TC_STAGES = 3;
+constexpr int TC_PRODUCERS = 256;            // 8 producer / epilogue warps
+constexpr int TC_THREADS = TC_PRODUCERS + 32;   // + the MMA warp
+constexpr int TC_A_BYTES = TC_ROWS * TC_K * 4;  // 32 KB (one of hi / lo)
+constexpr int TC_B_BYTES = 32 * TC_K * 4;       // 4 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;    // 72 KB
+constexpr int TC_TMEM_COLS = 128;            // 2 buffers x 2 tiles x 32 columns
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a protocol error traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    while (clock64() - t0 < 4000000000LL) {                 // ~2 s
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (the tensor core reads operands through it)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle: core matrices (8 rows x 16 B, 128 B contiguous) are
+// lbo bytes apart along K and sbo bytes apart along M/N (cute::UMMA::SmemDescriptor, version 1 = sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
+{
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float rest = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Y = X * Omega.  grid (gx, row blocks of 256): CTA (bx, by) takes the 32-column chunks bx, bx + gx, ... of its
+// rows and writes partial[bx][m][32]; sketch_reduce_kernel (ggp_rsvd.cu) sums the partials in FP64.
+template <bool VEC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __restrict__ OmT, int r, int k0,
+                 float* __restrict__ partial)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ uint32_t tmem_base_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row_base = blockIdx.y * TC_ROWS;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&full_bar[s], TC_PRODUCERS);
+        mbar_init(&tmem_full_bar[0], 1);
+        mbar_init(&tmem_full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    const long long nchunk = (n + TC_K - 1) / TC_K;
+    const int n_my = (blockIdx.x < nchunk) ? (int)((nchunk - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+
+    if (warp < 8) {
+        // ================= producers / epilogue =================
+        // A staging: item = warp*8 + u -> row group (8 rows) item/2, K half item%2; lane -> row lane%8, K piece lane/8
+        // B staging: thread -> Omega row (t/64)*8 + lane%8, K piece (t/8)%8
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+        const int b_row = (tid >> 6) * 8 + (lane & 7), b_kc = (tid >> 3) & 7;
+        const bool b_ok = (b_row < 32) && (k0 + b_row < r);
+        const uint32_t tile = warp >> 2;                                   // TMEM tile read by this warp
+        const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
+
+        for (int it = 0; it <= n_my; ++it) {
+            if (it < n_my) {
+                const long long c0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TC_K;
+                unsigned char* st = smem_raw + (size_t)(it % TC_STAGES) * TC_STAGE_BYTES;
+                float xv[8][4];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int item = warp * 8 + u;
+                    const int row = row_base + (item >> 1) * 8 + (lane & 7);
+                    const long long col = c0 + 4 * ((item & 1) * 4 + (lane >> 3));
+                    const float* src = X + (size_t)row * n + col;
+                    if (VEC && row < m && col + 3 < n) {
+                        const float4 q = __ldcs(reinterpret_cast<const float4*>(src));
+                        xv[u][0] = q.x; xv[u][1] = q.y; xv[u][2] = q.z; xv[u][3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xv[u][j] = (row < m && col + j < n) ? __ldcs(src + j) : 0.f;
+                    }
+                }
+                float bv[4];
+                {
+                    const long long col = c0 + 4 * b_kc;
+                    const float* src = OmT + (size_t)(k0 + b_row) * n + col;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bv[j] = (b_ok && col + j < n) ? __ldg(src + j) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int item = warp * 8 + u;
+                    const uint32_t off = (uint32_t)(item >> 1) * 1024u + (uint32_t)((item & 1) * 4 + (lane >> 3)) * 128u +
+                                         (uint32_t)(lane & 7) * 16u;
+                    uint4 hi, lo;
+                    split_tf32(xv[u][0], hi.x, lo.x);
+                    split_tf32(xv[u][1], hi.y, lo.y);
+                    split_tf32(xv[u][2], hi.z, lo.z);
+                    split_tf32(xv[u][3], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(st + off) = hi;
+                    *reinterpret_cast<uint4*>(st + TC_A_BYTES + off) = lo;
+                }
+                {
+                    const uint32_t off = (uint32_t)(b_row >> 3) * 1024u + (uint32_t)b_kc * 128u + (uint32_t)(b_row & 7) * 16u;
+                    uint4 hi, lo;
+                    split_tf32(bv[0], hi.x, lo.x);
+                    split_tf32(bv[1], hi.y, lo.y);
+                    split_tf32(bv[2], hi.z, lo.z);
+                    split_tf32(bv[3], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + off) = hi;
+                    *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + TC_B_BYTES + off) = lo;
+                }
+                fence_async_smem();
+                mbar_arrive(&full_bar[it % TC_STAGES]);
+            }
+            if (it >= 1) {
+                // chunk it-1 has been multiplied: add its TMEM tile into the register accumulators
+                const int j = it - 1;
+                mbar_wait(&tmem_full_bar[j & 1], (uint32_t)((j >> 1) & 1));
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32), v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v[c]);
+                tc_fence_before();
+            }
+        }
+        const int row = row_base + (int)tile * 128 + 32 * (warp & 3) + lane;
+        if (row < m) {
+            float4* out = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * m + row) * 32);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) out[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        }
+    } else if (lane == 0) {
+        // ================= MMA issuer (one thread) =================
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it % TC_STAGES;
+            mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE_BYTES);
+            const uint32_t a_lo = a_hi + TC_A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+            const uint32_t b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+            for (int tile = 0; tile < 2; ++tile) {
+                const uint32_t d = tmem_base + (uint32_t)((it & 1) * 64 + tile * 32);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint64_t ah = umma_desc(a_hi + tile * 16384 + t * 256, 128, 1024);
+                    const uint64_t al = umma_desc(a_lo + tile * 16384 + t * 256, 128, 1024);
+                    const uint64_t bh = umma_desc(b_hi + t * 256, 128, 1024);
+                    const uint64_t bl = umma_desc(b_lo + t * 256, 128, 1024);
+                    umma_tf32(d, al, bh, idesc, t > 0 ? 1u : 0u);      // small terms first
+                    umma_tf32(d, ah, bl, idesc, 1u);
+                    umma_tf32(d, ah, bh, idesc, 1u);
+                }
+            }
+            umma_commit(&tmem_full_bar[it & 1]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+    }
+}
+
+// fixed-order FP64 sum of the per-CTA partials [nparts][m][32] -> Y[m][r] columns k0 .. k0+31
+__global__ void tc_reduce_kernel(const float* __restrict__ partial, int nparts, int m, int r, int k0,
+                                 float* __restrict__ Y)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * 32) return;
+    const int row = idx >> 5, k = idx & 31;
+    if (k0 + k >= r) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * m * 32 + idx];
+    Y[(size_t)row * r + k0 + k] = (float)s;
+}
+
+static int tc_sm_count()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+}  // namespace ggp
+
+using namespace ggp;
+
+extern "C" {
+
+long long ggp_rsvd_tc_workspace_bytes(int m)
+{
+    if (m <= 0) return -1;
+    return (long long)tc_sm_count() * m * 32 * (long long)sizeof(float);
+}
+
+int ggp_rsvd_sketch_tc_f32(const float* X, int m, long long n, const float* OmegaT, int r, float* Y_out, void* workspace,
+                           long long workspace_bytes, void* stream)
+{
+    GGP_ARG(X && OmegaT && Y_out && workspace, "null pointer");
+    GGP_ARG(m > 0 && n > 0 && r > 0, "m, n, r must be positive");
+    if (workspace_bytes < ggp_rsvd_tc_workspace_bytes(m)) {
+        set_error("ggp_rsvd_sketch_tc_f32: workspace too small");
+        return GGP_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = reinterpret_cast<float*>(workspace);
+    const int gy = (m + TC_ROWS - 1) / TC_ROWS;
+    const long long nchunk = (n + TC_K - 1) / TC_K;
+    long long gx = tc_sm_count() / gy;                       // one CTA per SM (216 KB of shared memory each)
+    if (gx < 1) gx = 1;
+    if (gx > nchunk) gx = nchunk;
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES;
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int k0 = 0; k0 < r; k0 += 32) {
+        if (vec) sketch_tc_kernel<true><<<dim3((unsigned)gx, gy), TC_THREADS, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
+        else sketch_tc_kernel<false><<<dim3((unsigned)gx, gy), TC_THREADS, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
+        GGP_CUDA(cudaGetLastError());
+        tc_reduce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(partial, (int)gx, m, r, k0, Y_out);
+        GGP_CUDA(cudaGetLastError());
+    }
+    return GGP_OK;
+}
+
+}  // extern "C"

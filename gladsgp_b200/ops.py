@@ -359,3 +359,18 @@ def project(X, Kt):
     P = torch.empty((m, pu + 2), dtype=torch.float64, device='cuda')
     check(lib.ggp_project_f32(ptr(X), m, n, ptr(Kt), pu, ptr(P), ptr(ws), ws.numel(), stream_ptr()), 'ggp_project_f32')
     return P
+
+
+def rsvd_sketch_tc(X, omegaT, ws=None):
+    """Y = X @ omega on the tcgen05 tensor cores (3xTF32 split, FP32-level accuracy); any m."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    m, n = X.shape
+    r = omegaT.shape[0]
+    need = lib.ggp_rsvd_tc_workspace_bytes(m)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device='cuda')
+    Y = torch.empty((m, r), dtype=torch.float32, device='cuda')
+    check(lib.ggp_rsvd_sketch_tc_f32(ptr(X), m, n, ptr(omegaT), r, ptr(Y), ptr(ws), ws.numel(), stream_ptr()),
+          'ggp_rsvd_sketch_tc_f32')
+    return Y

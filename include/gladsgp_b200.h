@@ -163,6 +163,11 @@ long long ggp_rsvd_workspace_bytes(int m);
 int ggp_rsvd_sketch_f32(const float* X, int m, long long n, const float* OmegaT, int r, float* Y_out,
                         void* workspace, long long workspace_bytes, void* stream);
 int ggp_rsvd_xty_f32(const float* X, int m, long long n, const float* Y, int r, float* Bt_out, void* stream);
+/* The same products on the tcgen05 tensor cores (3xTF32 split, FP32-level accuracy; csrc/ggp_rsvd_tc.cu): bound by
+ * the HBM read of X instead of the FP32 FMA rate.  Any m.  workspace: ggp_rsvd_tc_workspace_bytes(m). */
+long long ggp_rsvd_tc_workspace_bytes(int m);
+int ggp_rsvd_sketch_tc_f32(const float* X, int m, long long n, const float* OmegaT, int r, float* Y_out,
+                           void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- (5) ensemble ingest and initialisation passes ------------------------------
  * The streaming work of init_model / fit_models around the PCA, on the (m x n) float32 ensemble:
