@@ -10,7 +10,7 @@
 // over n never runs inside the tensor core.
 //
 // Operands are staged by the producer warps: global -> registers (split hi/lo) -> shared memory in the UMMA
-// canonical K-major no-swizzle layout (core matrix = 8 rows x 16 bytes; TMA cannot be used because the row pitch of
+// canonical K-major 128-byte-swizzle layout (the one TMA would write; TMA cannot be used because the row pitch of
 // the reference's ensembles, 4*n_y bytes with n_y = 3693*365, is not a multiple of 16 bytes).  One elected thread of
 // the MMA warp issues tcgen05.mma and signals completion with tcgen05.commit on an mbarrier.
 #include "ggp_common.cuh"
@@ -21,8 +21,8 @@ namespace ggp {
 constexpr int TC_ROWS = 256;                 // rows of X per CTA (two M = 128 tiles)
 constexpr int TC_K = 32;                     // columns of X per chunk (four K = 8 steps)
 constexpr int TC_STAGES = 3;
-constexpr int TC_PRODUCERS = 256;            // 8 producer / epilogue warps
-constexpr int TC_THREADS = TC_PRODUCERS + 32;   // + the MMA warp
+constexpr int TC_PRODUCERS = 256;            // 8 producer warps
+constexpr int TC_THREADS = TC_PRODUCERS + 128;  // + 4 epilogue warps (the first one also issues the MMAs)
 constexpr int TC_A_BYTES = TC_ROWS * TC_K * 4;  // 32 KB (one of hi / lo)
 constexpr int TC_B_BYTES = 32 * TC_K * 4;       // 4 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;    // 72 KB
@@ -42,15 +42,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    while (clock64() - t0 < 4000000000LL) {                 // ~2 s
+    for (int spin = 0; spin < 4000; ++spin) {               // each try_wait may suspend the thread for up to 1 ms
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(1000000u)
             : "memory");
         if (ok) return;
     }
@@ -68,6 +67,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// K-major, 128-byte swizzle: a row is 128 contiguous bytes (32 tf32 = one K chunk), rows 128 B apart, 8-row groups
+// 1024 B apart, and the 16-byte piece kc of row r sits at position kc ^ (r % 8) (Swizzle<3,4,3>; tile 1024-B aligned).
+// A K = 8 step advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
@@ -111,7 +117,15 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
 
 // ---------------------------------------------------------------------------------------------------------
 // Y = X * Omega.  grid (gx, row blocks of 256): CTA (bx, by) takes the 32-column chunks bx, bx + gx, ... of its
-// rows and writes partial[bx][m][32]; sketch_reduce_kernel (ggp_rsvd.cu) sums the partials in FP64.
+// rows and writes partial[bx][m][32]; tc_reduce_kernel sums the partials in FP64 in a fixed order.
+//
+// Warp roles (12 warps, 168 registers each = 3 warps per SM sub-partition):
+//   warps 0-7   producers: global -> registers (two chunks ahead, three rotating buffers) -> hi/lo split -> swizzled
+//               shared-memory stage -> fence.proxy.async -> arrive on full[stage]
+//   warp 8      lane 0 issues the 24 tcgen05.mma of a chunk (2 M-tiles x 4 K-steps x 3 split products) and commits
+//               to empty[stage] (stage reusable) and tmem_full[buffer] (chunk sum ready)
+//   warps 8-11  epilogue: tcgen05.ld the chunk sum (two 128 x 32 tiles, TMEM double-buffered) and add it to FP32
+//               register accumulators with round-to-nearest
 template <bool VEC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __restrict__ OmT, int r, int k0,
@@ -119,13 +133,17 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ uint32_t tmem_base_sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row_base = blockIdx.y * TC_ROWS;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&full_bar[s], TC_PRODUCERS);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], TC_PRODUCERS);
+            mbar_init(&empty_bar[s], 1);
+        }
         mbar_init(&tmem_full_bar[0], 1);
         mbar_init(&tmem_full_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,116 +159,174 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
     const uint32_t tmem_base = tmem_base_sh;
 
     const long long nchunk = (n + TC_K - 1) / TC_K;
+#ifdef GGP_TC_INTERLEAVE
     const int n_my = (blockIdx.x < nchunk) ? (int)((nchunk - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    auto chunk_col = [&](int it) { return ((long long)blockIdx.x + (long long)it * gridDim.x) * TC_K; };
+#else
+    // a contiguous range of chunks per CTA: successive loads of a thread walk along one row of X
+    const long long per = (nchunk + gridDim.x - 1) / gridDim.x;
+    const long long ch_begin = (long long)blockIdx.x * per;
+    const int n_my = (int)(ch_begin >= nchunk ? 0 : (nchunk - ch_begin < per ? nchunk - ch_begin : per));
+    auto chunk_col = [&](int it) { return (ch_begin + it) * TC_K; };
+#endif
 
     if (warp < 8) {
-        // ================= producers / epilogue =================
-        // A staging: item = warp*8 + u -> row group (8 rows) item/2, K half item%2; lane -> row lane%8, K piece lane/8
-        // B staging: thread -> Omega row (t/64)*8 + lane%8, K piece (t/8)%8
-        float acc[32];
+        // ================= producers =================
+        // A staging: warp w, pass u, lane l -> row 32 w + 4 u + l/8, 16-byte K piece l%8 (full 128-byte lines from
+        // global, conflict-free STS.128 into the swizzled tile).  B staging: thread t -> Omega row t/8, K piece t%8.
+        const int b_row = tid >> 3, b_kc = tid & 7;
+        const bool b_ok = (k0 + b_row < r);
+        const int lrow0 = warp * 32 + (lane >> 3);                         // local row of pass 0 (pass u: + 4 u)
+        const float* xp = X + (size_t)(row_base + lrow0) * n + 4 * (lane & 7);      // + 4 u n + c0
+        const float* bp = OmT + (size_t)(k0 + (b_ok ? b_row : 0)) * n + 4 * b_kc;
+        const size_t pass_stride = 4 * (size_t)n;
+        unsigned row_ok = 0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-        const int b_row = (tid >> 6) * 8 + (lane & 7), b_kc = (tid >> 3) & 7;
-        const bool b_ok = (b_row < 32) && (k0 + b_row < r);
-        const uint32_t tile = warp >> 2;                                   // TMEM tile read by this warp
-        const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
+        for (int u = 0; u < 8; ++u) row_ok |= (row_base + lrow0 + 4 * u < m) ? (1u << u) : 0u;
 
-        for (int it = 0; it <= n_my; ++it) {
-            if (it < n_my) {
-                const long long c0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TC_K;
-                unsigned char* st = smem_raw + (size_t)(it % TC_STAGES) * TC_STAGE_BYTES;
-                float xv[8][4];
+        auto load_chunk = [&](int it, float (&xv)[8][4], float (&bv)[4]) {
+            const long long c0 = chunk_col(it);
+            const float* src0 = xp + c0;
+            if (c0 + TC_K <= n) {                               // whole chunk inside the matrix (CTA-uniform)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int item = warp * 8 + u;
-                    const int row = row_base + (item >> 1) * 8 + (lane & 7);
-                    const long long col = c0 + 4 * ((item & 1) * 4 + (lane >> 3));
-                    const float* src = X + (size_t)row * n + col;
-                    if (VEC && row < m && col + 3 < n) {
+                    const float* src = src0 + u * pass_stride;
+                    if (!((row_ok >> u) & 1)) {
+                        xv[u][0] = 0.f; xv[u][1] = 0.f; xv[u][2] = 0.f; xv[u][3] = 0.f;
+                    } else if (VEC) {
                         const float4 q = __ldcs(reinterpret_cast<const float4*>(src));
                         xv[u][0] = q.x; xv[u][1] = q.y; xv[u][2] = q.z; xv[u][3] = q.w;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) xv[u][j] = (row < m && col + j < n) ? __ldcs(src + j) : 0.f;
+                        for (int j = 0; j < 4; ++j) xv[u][j] = __ldcs(src + j);
                     }
                 }
-                float bv[4];
-                {
-                    const long long col = c0 + 4 * b_kc;
-                    const float* src = OmT + (size_t)(k0 + b_row) * n + col;
+                if (!b_ok) {
+                    bv[0] = 0.f; bv[1] = 0.f; bv[2] = 0.f; bv[3] = 0.f;
+                } else if (VEC) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(bp + c0));
+                    bv[0] = q.x; bv[1] = q.y; bv[2] = q.z; bv[3] = q.w;
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) bv[j] = (b_ok && col + j < n) ? __ldg(src + j) : 0.f;
+                    for (int j = 0; j < 4; ++j) bv[j] = __ldg(bp + c0 + j);
                 }
+            } else {                                            // ragged last chunk
+                const long long col = c0 + 4 * (lane & 7);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int item = warp * 8 + u;
-                    const uint32_t off = (uint32_t)(item >> 1) * 1024u + (uint32_t)((item & 1) * 4 + (lane >> 3)) * 128u +
-                                         (uint32_t)(lane & 7) * 16u;
-                    uint4 hi, lo;
-                    split_tf32(xv[u][0], hi.x, lo.x);
-                    split_tf32(xv[u][1], hi.y, lo.y);
-                    split_tf32(xv[u][2], hi.z, lo.z);
-                    split_tf32(xv[u][3], hi.w, lo.w);
-                    *reinterpret_cast<uint4*>(st + off) = hi;
-                    *reinterpret_cast<uint4*>(st + TC_A_BYTES + off) = lo;
-                }
-                {
-                    const uint32_t off = (uint32_t)(b_row >> 3) * 1024u + (uint32_t)b_kc * 128u + (uint32_t)(b_row & 7) * 16u;
-                    uint4 hi, lo;
-                    split_tf32(bv[0], hi.x, lo.x);
-                    split_tf32(bv[1], hi.y, lo.y);
-                    split_tf32(bv[2], hi.z, lo.z);
-                    split_tf32(bv[3], hi.w, lo.w);
-                    *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + off) = hi;
-                    *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + TC_B_BYTES + off) = lo;
-                }
-                fence_async_smem();
-                mbar_arrive(&full_bar[it % TC_STAGES]);
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        xv[u][j] = (((row_ok >> u) & 1) && col + j < n) ? __ldcs(src0 + u * pass_stride + j) : 0.f;
+                const long long colb = c0 + 4 * b_kc;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = (b_ok && colb + j < n) ? __ldg(bp + c0 + j) : 0.f;
             }
+        };
+        // one pipeline step: chunk `it` is in (xv, bv); chunk it+2 is loaded into (xl, bl)
+        auto step = [&](int it, float (&xv)[8][4], float (&bv)[4], float (&xl)[8][4], float (&bl)[4]) {
+            if (it >= n_my) return;
+            if (it + 2 < n_my) load_chunk(it + 2, xl, bl);
+            const int s = it % TC_STAGES;
+            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / TC_STAGES - 1) & 1));   // MMAs of chunk it-3 done
+            unsigned char* st = smem_raw + (size_t)s * TC_STAGE_BYTES;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t lrow = (uint32_t)(lrow0 + 4 * u);
+                const uint32_t off = lrow * 128u + (uint32_t)(((lane & 7) ^ (lrow & 7)) * 16);
+                uint4 hi, lo;
+                split_tf32(xv[u][0], hi.x, lo.x);
+                split_tf32(xv[u][1], hi.y, lo.y);
+                split_tf32(xv[u][2], hi.z, lo.z);
+                split_tf32(xv[u][3], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + TC_A_BYTES + off) = lo;
+            }
+            {
+                const uint32_t off = (uint32_t)b_row * 128u + (uint32_t)((b_kc ^ (b_row & 7)) * 16);
+                uint4 hi, lo;
+                split_tf32(bv[0], hi.x, lo.x);
+                split_tf32(bv[1], hi.y, lo.y);
+                split_tf32(bv[2], hi.z, lo.z);
+                split_tf32(bv[3], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + off) = hi;
+                *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + TC_B_BYTES + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(&full_bar[s]);
+        };
+        float x0[8][4], x1[8][4], x2[8][4], b0[4], b1[4], b2[4];
+        if (n_my > 0) load_chunk(0, x0, b0);
+        if (n_my > 1) load_chunk(1, x1, b1);
+#pragma unroll 1
+        for (int it = 0; it < n_my; it += 3) {
+            step(it, x0, b0, x2, b2);
+            step(it + 1, x1, b1, x0, b0);
+            step(it + 2, x2, b2, x1, b1);
+        }
+    } else {
+        // ================= MMA issue (warp 8, lane 0) + epilogue (warps 8-11) =================
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
+        const int ew = warp - 8;                                             // TMEM lanes 32 ew .. 32 ew + 31
+        const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
+        float acc[2][32];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[t][c] = 0.f;
+#pragma unroll 1
+        for (int it = 0; it <= n_my; ++it) {
+            if (it < n_my && warp == 8 && lane == 0) {
+                const int s = it % TC_STAGES;
+                mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE_BYTES);
+                const uint32_t a_lo = a_hi + TC_A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+                const uint32_t b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+                for (int tile = 0; tile < 2; ++tile) {
+                    const uint32_t d = tmem_base + (uint32_t)((it & 1) * 64 + tile * 32);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint64_t ah = umma_desc_sw128(a_hi + tile * 16384 + t * 32);
+                        const uint64_t al = umma_desc_sw128(a_lo + tile * 16384 + t * 32);
+                        const uint64_t bh = umma_desc_sw128(b_hi + t * 32);
+                        const uint64_t bl = umma_desc_sw128(b_lo + t * 32);
+                        umma_tf32(d, al, bh, idesc, t > 0 ? 1u : 0u);      // small terms first
+                        umma_tf32(d, ah, bl, idesc, 1u);
+                        umma_tf32(d, ah, bh, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+                umma_commit(&tmem_full_bar[it & 1]);
+            }
+            __syncwarp();
             if (it >= 1) {
-                // chunk it-1 has been multiplied: add its TMEM tile into the register accumulators
+                // chunk it-1 has been multiplied: add its TMEM tiles into the register accumulators
                 const int j = it - 1;
                 mbar_wait(&tmem_full_bar[j & 1], (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32), v);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v[c]);
+                for (int tile = 0; tile < 2; ++tile) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32), v);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[tile][c] += __uint_as_float(v[c]);
+                }
                 tc_fence_before();
             }
+            // all four epilogue warps are done with TMEM buffer (it-1)&1 before the MMAs of chunk it+1 overwrite it
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        const int row = row_base + (int)tile * 128 + 32 * (warp & 3) + lane;
-        if (row < m) {
-            float4* out = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * m + row) * 32);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) out[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-        }
-    } else if (lane == 0) {
-        // ================= MMA issuer (one thread) =================
-        constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
-        for (int it = 0; it < n_my; ++it) {
-            const int s = it % TC_STAGES;
-            mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE_BYTES);
-            const uint32_t a_lo = a_hi + TC_A_BYTES;
-            const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
-            const uint32_t b_lo = b_hi + TC_B_BYTES;
+        for (int tile = 0; tile < 2; ++tile) {
+            const int row = row_base + tile * 128 + 32 * ew + lane;
+            if (row < m) {
+                float4* out = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * m + row) * 32);
 #pragma unroll
-            for (int tile = 0; tile < 2; ++tile) {
-                const uint32_t d = tmem_base + (uint32_t)((it & 1) * 64 + tile * 32);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint64_t ah = umma_desc(a_hi + tile * 16384 + t * 256, 128, 1024);
-                    const uint64_t al = umma_desc(a_lo + tile * 16384 + t * 256, 128, 1024);
-                    const uint64_t bh = umma_desc(b_hi + t * 256, 128, 1024);
-                    const uint64_t bl = umma_desc(b_lo + t * 256, 128, 1024);
-                    umma_tf32(d, al, bh, idesc, t > 0 ? 1u : 0u);      // small terms first
-                    umma_tf32(d, ah, bl, idesc, 1u);
-                    umma_tf32(d, ah, bh, idesc, 1u);
-                }
+                for (int c = 0; c < 8; ++c)
+                    out[c] = make_float4(acc[tile][4 * c], acc[tile][4 * c + 1], acc[tile][4 * c + 2], acc[tile][4 * c + 3]);
             }
-            umma_commit(&tmem_full_bar[it & 1]);
         }
     }
     tc_fence_before();

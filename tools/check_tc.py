@@ -7,6 +7,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gladsgp_b200 import _lib  # noqa: E402
+if os.environ.get('GGP_LIB'):
+    _lib.LIB_PATH = os.path.abspath(os.environ['GGP_LIB'])
 from gladsgp_b200 import ops  # noqa: E402
 
 
