@@ -59,6 +59,7 @@ SIGNATURES = {
     'ggp_rsvd_xty_f32': (_I, [_P, _I, _LL, _P, _I, _P, _P]),
     'ggp_rsvd_tc_workspace_bytes': (_LL, [_I]),
     'ggp_rsvd_sketch_tc_f32': (_I, [_P, _I, _LL, _P, _I, _P, _P, _LL, _P]),
+    'ggp_rsvd_xty_tc_f32': (_I, [_P, _I, _LL, _P, _I, _P, _P]),
     'ggp_colstats_f32': (_I, [_P, _LL, _I, _LL, _I, _I, _F, _P, _P, _P]),
     'ggp_standardize_f32': (_I, [_P, _LL, _I, _LL, _I, _P, _LL, _P, _LL, _P, _P]),
     'ggp_project_workspace_bytes': (_LL, [_I, _I]),

@@ -28,6 +28,10 @@ constexpr int TC_B_BYTES = 32 * TC_K * 4;       // 4 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;    // 72 KB
 constexpr int TC_TMEM_COLS = 128;            // 2 buffers x 2 tiles x 32 columns
 
+#ifndef GGP_TC_LD
+#define GGP_TC_LD __ldcs
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -74,6 +78,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major 32-bit operands have one legal layout, "128-byte swizzle with 32-byte base" (cute Layout_MN_SW128_32B_Atom,
+// Swizzle<2,5,2>): 32 consecutive M (or N) elements of one k per 128-byte line, four k per 512-byte atom, the 32-byte
+// unit u of line k stored at position u ^ (k % 4); atoms of the next 32 M elements are lbo bytes apart, atoms of the
+// next four k are sbo bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
@@ -194,7 +207,7 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
                     if (!((row_ok >> u) & 1)) {
                         xv[u][0] = 0.f; xv[u][1] = 0.f; xv[u][2] = 0.f; xv[u][3] = 0.f;
                     } else if (VEC) {
-                        const float4 q = __ldcs(reinterpret_cast<const float4*>(src));
+                        const float4 q = GGP_TC_LD(reinterpret_cast<const float4*>(src));
                         xv[u][0] = q.x; xv[u][1] = q.y; xv[u][2] = q.z; xv[u][3] = q.w;
                     } else {
 #pragma unroll
@@ -337,6 +350,200 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bt = Y^T X  (Bt[r][n]).  The output column block (256 columns = two M = 128 tiles) is the MMA's M dimension and
+// the m rows are K:  D[c][k] = sum_i X[i][c] * Y[i][k].  X is row-major, i.e. contiguous along M, so the A operand
+// is staged MN-major (32 consecutive columns of one row per 128-byte line, four rows per 512-byte swizzle atom) --
+// each warp load instruction reads 512 contiguous bytes of a row.  Y (m x r, L2-resident) is staged
+// K-major like Omega above.  A CTA walks down the rows of its column block in 32-row chunks, adds each chunk's TMEM
+// tile into FP32 registers and writes the block out after the last chunk.
+template <bool VEC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __restrict__ Y, int r, int k0,
+              float* __restrict__ Bt)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ uint32_t tmem_base_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], TC_PRODUCERS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar[0], 1);
+        mbar_init(&tmem_full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    const int nk = (m + 31) / 32;                                           // K chunks per column block
+    const long long nblk = (n + TC_ROWS - 1) / TC_ROWS;                     // column blocks of 256
+    const int blk_my = (blockIdx.x < nblk) ? (int)((nblk - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    const int n_my = blk_my * nk;
+    auto blk_col = [&](int b) { return ((long long)blockIdx.x + (long long)b * gridDim.x) * TC_ROWS; };
+
+    if (warp < 8) {
+        // ================= producers =================
+        // A staging: item = 8 w + u -> row of the chunk item/2, tile item%2; lane -> columns 4 l .. 4 l + 3 of the tile.
+        // B staging: thread t -> output row (k index) t/8, four consecutive rows of the chunk 4 (t%8) ..
+        const int b_n = tid >> 3, b_kc = tid & 7;
+        const bool b_ok = (k0 + b_n < r);
+        auto load_chunk = [&](int it, float (&xv)[8][4], float (&bv)[4]) {
+            const int b = it / nk, kc = it - b * nk;
+            const long long c0 = blk_col(b);
+            const int i0 = kc * 32;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int item = warp * 8 + u;
+                const int row = i0 + (item >> 1);
+                const long long col = c0 + (item & 1) * 128 + 4 * lane;
+                const float* src = X + (size_t)row * n + col;
+                if (row >= m || col >= n) {
+                    xv[u][0] = 0.f; xv[u][1] = 0.f; xv[u][2] = 0.f; xv[u][3] = 0.f;
+                } else if (VEC) {                                   // n % 4 == 0: col + 3 < n
+                    const float4 q = GGP_TC_LD(reinterpret_cast<const float4*>(src));
+                    xv[u][0] = q.x; xv[u][1] = q.y; xv[u][2] = q.z; xv[u][3] = q.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xv[u][j] = (col + j < n) ? __ldcs(src + j) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = i0 + 4 * b_kc + j;
+                bv[j] = (b_ok && row < m) ? __ldg(Y + (size_t)row * r + k0 + b_n) : 0.f;
+            }
+        };
+        auto step = [&](int it, float (&xv)[8][4], float (&bv)[4], float (&xl)[8][4], float (&bl)[4]) {
+            if (it >= n_my) return;
+            if (it + 2 < n_my) load_chunk(it + 2, xl, bl);
+            const int s = it % TC_STAGES;
+            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / TC_STAGES - 1) & 1));
+            unsigned char* st = smem_raw + (size_t)s * TC_STAGE_BYTES;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int item = warp * 8 + u;
+                const uint32_t krow = (uint32_t)(item >> 1);
+                const uint32_t gmb = (uint32_t)((item & 1) * 4 + (lane >> 3));
+                const uint32_t off = gmb * 4096u + (krow >> 2) * 512u + (krow & 3) * 128u +
+                                     (uint32_t)((((lane & 7) >> 1) ^ (krow & 3)) * 32 + (lane & 1) * 16);
+                uint4 hi, lo;
+                split_tf32(xv[u][0], hi.x, lo.x);
+                split_tf32(xv[u][1], hi.y, lo.y);
+                split_tf32(xv[u][2], hi.z, lo.z);
+                split_tf32(xv[u][3], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + TC_A_BYTES + off) = lo;
+            }
+            {
+                const uint32_t off = (uint32_t)b_n * 128u + (uint32_t)((b_kc ^ (b_n & 7)) * 16);
+                uint4 hi, lo;
+                split_tf32(bv[0], hi.x, lo.x);
+                split_tf32(bv[1], hi.y, lo.y);
+                split_tf32(bv[2], hi.z, lo.z);
+                split_tf32(bv[3], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + off) = hi;
+                *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + TC_B_BYTES + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(&full_bar[s]);
+        };
+        float x0[8][4], x1[8][4], x2[8][4], b0[4], b1[4], b2[4];
+        if (n_my > 0) load_chunk(0, x0, b0);
+        if (n_my > 1) load_chunk(1, x1, b1);
+#pragma unroll 1
+        for (int it = 0; it < n_my; it += 3) {
+            step(it, x0, b0, x2, b2);
+            step(it + 1, x1, b1, x0, b0);
+            step(it + 2, x2, b2, x1, b1);
+        }
+    } else {
+        // ================= MMA issue (warp 8, lane 0) + epilogue (warps 8-11) =================
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 32) | (1u << 15);      // A is MN-major
+        const int ew = warp - 8;
+        const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
+        float acc[2][32];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[t][c] = 0.f;
+#pragma unroll 1
+        for (int it = 0; it <= n_my; ++it) {
+            if (it < n_my && warp == 8 && lane == 0) {
+                const int s = it % TC_STAGES;
+                mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE_BYTES);
+                const uint32_t a_lo = a_hi + TC_A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+                const uint32_t b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+                for (int tile = 0; tile < 2; ++tile) {
+                    const uint32_t d = tmem_base + (uint32_t)((it & 1) * 64 + tile * 32);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint64_t ah = umma_desc_mn_sw128_32b(a_hi + tile * 16384 + t * 1024, 4096, 512);
+                        const uint64_t al = umma_desc_mn_sw128_32b(a_lo + tile * 16384 + t * 1024, 4096, 512);
+                        const uint64_t bh = umma_desc_sw128(b_hi + t * 32);
+                        const uint64_t bl = umma_desc_sw128(b_lo + t * 32);
+                        umma_tf32(d, al, bh, idesc, t > 0 ? 1u : 0u);
+                        umma_tf32(d, ah, bl, idesc, 1u);
+                        umma_tf32(d, ah, bh, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+                umma_commit(&tmem_full_bar[it & 1]);
+            }
+            __syncwarp();
+            if (it >= 1) {
+                const int j = it - 1;
+                mbar_wait(&tmem_full_bar[j & 1], (uint32_t)((j >> 1) & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int tile = 0; tile < 2; ++tile) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32), v);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[tile][c] += __uint_as_float(v[c]);
+                }
+                tc_fence_before();
+                if ((j + 1) % nk == 0) {
+                    // last chunk of a column block: write Bt[k0 + c][col] and restart the sums
+                    const long long c0 = blk_col(j / nk);
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const long long col = c0 + tile * 128 + 32 * ew + lane;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (col < n && k0 + c < r) __stcs(Bt + (size_t)(k0 + c) * n + col, acc[tile][c]);
+                            acc[tile][c] = 0.f;
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+    }
+}
+
 // fixed-order FP64 sum of the per-CTA partials [nparts][m][32] -> Y[m][r] columns k0 .. k0+31
 __global__ void tc_reduce_kernel(const float* __restrict__ partial, int nparts, int m, int r, int k0,
                                  float* __restrict__ Y)
@@ -395,6 +602,26 @@ int ggp_rsvd_sketch_tc_f32(const float* X, int m, long long n, const float* Omeg
         else sketch_tc_kernel<false><<<dim3((unsigned)gx, gy), TC_THREADS, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
         GGP_CUDA(cudaGetLastError());
         tc_reduce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(partial, (int)gx, m, r, k0, Y_out);
+        GGP_CUDA(cudaGetLastError());
+    }
+    return GGP_OK;
+}
+
+int ggp_rsvd_xty_tc_f32(const float* X, int m, long long n, const float* Y, int r, float* Bt_out, void* stream)
+{
+    GGP_ARG(X && Y && Bt_out, "null pointer");
+    GGP_ARG(m > 0 && n > 0 && r > 0, "m, n, r must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nblk = (n + TC_ROWS - 1) / TC_ROWS;
+    long long gx = tc_sm_count();
+    if (gx > nblk) gx = nblk;
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES;
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    GGP_CUDA(cudaFuncSetAttribute(xty_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(xty_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int k0 = 0; k0 < r; k0 += 32) {
+        if (vec) xty_tc_kernel<true><<<(unsigned)gx, TC_THREADS, smem, st>>>(X, m, n, Y, r, k0, Bt_out);
+        else xty_tc_kernel<false><<<(unsigned)gx, TC_THREADS, smem, st>>>(X, m, n, Y, r, k0, Bt_out);
         GGP_CUDA(cudaGetLastError());
     }
     return GGP_OK;

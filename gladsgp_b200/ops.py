@@ -374,3 +374,14 @@ def rsvd_sketch_tc(X, omegaT, ws=None):
     check(lib.ggp_rsvd_sketch_tc_f32(ptr(X), m, n, ptr(omegaT), r, ptr(Y), ptr(ws), ws.numel(), stream_ptr()),
           'ggp_rsvd_sketch_tc_f32')
     return Y
+
+
+def rsvd_xty_tc(X, Y):
+    """Bt (r,n) = Y^T X on the tcgen05 tensor cores (3xTF32 split); any m."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    m, n = X.shape
+    r = Y.shape[1]
+    Bt = torch.empty((r, n), dtype=torch.float32, device='cuda')
+    check(lib.ggp_rsvd_xty_tc_f32(ptr(X), m, n, ptr(Y.contiguous()), r, ptr(Bt), stream_ptr()), 'ggp_rsvd_xty_tc_f32')
+    return Bt

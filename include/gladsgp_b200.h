@@ -168,6 +168,7 @@ int ggp_rsvd_xty_f32(const float* X, int m, long long n, const float* Y, int r, 
 long long ggp_rsvd_tc_workspace_bytes(int m);
 int ggp_rsvd_sketch_tc_f32(const float* X, int m, long long n, const float* OmegaT, int r, float* Y_out,
                            void* workspace, long long workspace_bytes, void* stream);
+int ggp_rsvd_xty_tc_f32(const float* X, int m, long long n, const float* Y, int r, float* Bt_out, void* stream);
 
 /* ---- (5) ensemble ingest and initialisation passes ------------------------------
  * The streaming work of init_model / fit_models around the PCA, on the (m x n) float32 ensemble:

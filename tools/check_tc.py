@@ -37,8 +37,15 @@ def main():
         e_simt = None
         if m <= 1024:
             e_simt = float(np.abs(ops.rsvd_sketch(Xd, Od).cpu().numpy() - ref).max() / scale)
-        res['%dx%dx%d' % (m, n, r)] = dict(err_tc=e_tc, err_simt=e_simt)
-        print(m, n, r, 'err tc', e_tc, 'simt', e_simt, flush=True)
+        # xty: Bt = Y^T X with Y (m, r)
+        Yh = rng.standard_normal((m, r)).astype(np.float32)
+        Yd = torch.as_tensor(Yh, device='cuda')
+        refb = Yh.astype(np.float64).T @ X.astype(np.float64)
+        sb = np.abs(refb).max()
+        ex_tc = float(np.abs(ops.rsvd_xty_tc(Xd, Yd).cpu().numpy() - refb).max() / sb)
+        ex_simt = float(np.abs(ops.rsvd_xty(Xd, Yd).cpu().numpy() - refb).max() / sb) if m <= 1024 else None
+        res['%dx%dx%d' % (m, n, r)] = dict(err_tc=e_tc, err_simt=e_simt, xty_err_tc=ex_tc, xty_err_simt=ex_simt)
+        print(m, n, r, 'sketch err tc', e_tc, 'simt', e_simt, '| xty err tc', ex_tc, 'simt', ex_simt, flush=True)
     if '--time' in sys.argv:
         m, n, r = 512, 1460000, 25
         Xd = torch.randn((m, n), dtype=torch.float32, device='cuda')
@@ -48,6 +55,10 @@ def main():
         res['time_ms'] = dict(tc=t_tc, simt=t_simt, tc_gbs=4.0 * m * n / t_tc / 1e6, simt_gbs=4.0 * m * n / t_simt / 1e6)
         d = (ops.rsvd_sketch_tc(Xd, Od) - ops.rsvd_sketch(Xd, Od)).abs().max().item()
         res['tc_vs_simt_maxabs'] = d
+        Yd = torch.randn((m, r), dtype=torch.float32, device='cuda')
+        t_tc = ev(lambda: ops.rsvd_xty_tc(Xd, Yd))
+        t_simt = ev(lambda: ops.rsvd_xty(Xd, Yd))
+        res['xty_time_ms'] = dict(tc=t_tc, simt=t_simt, tc_gbs=4.0 * m * n / t_tc / 1e6, simt_gbs=4.0 * m * n / t_simt / 1e6)
     print(json.dumps(res))
 
 
