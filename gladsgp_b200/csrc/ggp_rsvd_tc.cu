@@ -65,28 +65,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // generic-proxy shared-memory writes -> visible to the async proxy (the tensor core reads operands through it)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, K-major, no swizzle: core matrices (8 rows x 16 B, 128 B contiguous) are
-// lbo bytes apart along K and sbo bytes apart along M/N (cute::UMMA::SmemDescriptor, version 1 = sm_100).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
 // K-major, 128-byte swizzle: a row is 128 contiguous bytes (32 tf32 = one K chunk), rows 128 B apart, 8-row groups
 // 1024 B apart, and the 16-byte piece kc of row r sits at position kc ^ (r % 8) (Swizzle<3,4,3>; tile 1024-B aligned).
 // A K = 8 step advances the start address by 32 bytes.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// MN-major 32-bit operands have one legal layout, "128-byte swizzle with 32-byte base" (cute Layout_MN_SW128_32B_Atom,
-// Swizzle<2,5,2>): 32 consecutive M (or N) elements of one k per 128-byte line, four k per 512-byte atom, the 32-byte
-// unit u of line k stored at position u ^ (k % 4); atoms of the next 32 M elements are lbo bytes apart, atoms of the
-// next four k are sbo bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
@@ -121,11 +105,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// x = hi + lo with hi on the TF32 grid (round to nearest, ties away -- what cvt.rna.tf32.f32 does, but on the integer
+// pipe: the conversion instruction runs on the quarter-rate XU pipe and was the producers' bottleneck) and lo = x - hi
+// exact in FP32 (|lo| <= 2^-11 |x|); the tensor core reads the upper 19 bits of lo (error <= 2^-21 |x|).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
 {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float rest = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -139,8 +136,8 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
 //               to empty[stage] (stage reusable) and tmem_full[buffer] (chunk sum ready)
 //   warps 8-11  epilogue: tcgen05.ld the chunk sum (two 128 x 32 tiles, TMEM double-buffered) and add it to FP32
 //               register accumulators with round-to-nearest
-template <bool VEC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool VEC, int NPW>
+__global__ void __launch_bounds__(NPW * 32 + 128, 1)
 sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __restrict__ OmT, int r, int k0,
                  float* __restrict__ partial)
 {
@@ -154,14 +151,14 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(&full_bar[s], TC_PRODUCERS);
+            mbar_init(&full_bar[s], NPW * 32);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&tmem_full_bar[0], 1);
         mbar_init(&tmem_full_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == NPW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
                      "r"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -183,26 +180,28 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
     auto chunk_col = [&](int it) { return (ch_begin + it) * TC_K; };
 #endif
 
-    if (warp < 8) {
+    if (warp < NPW) {
         // ================= producers =================
         // A staging: warp w, pass u, lane l -> row 32 w + 4 u + l/8, 16-byte K piece l%8 (full 128-byte lines from
         // global, conflict-free STS.128 into the swizzled tile).  B staging: thread t -> Omega row t/8, K piece t%8.
-        const int b_row = tid >> 3, b_kc = tid & 7;
-        const bool b_ok = (k0 + b_row < r);
-        const int lrow0 = warp * 32 + (lane >> 3);                         // local row of pass 0 (pass u: + 4 u)
+        constexpr int UP = 64 / NPW;                                       // 128-byte row pieces per thread and chunk
+        const bool b_thread = tid < 256;                                   // threads that also stage Omega
+        const int b_row = (tid >> 3) & 31, b_kc = tid & 7;
+        const bool b_ok = b_thread && (k0 + b_row < r);
+        const int lrow0 = warp * (4 * UP) + (lane >> 3);                         // local row of pass 0 (pass u: + 4 u)
         const float* xp = X + (size_t)(row_base + lrow0) * n + 4 * (lane & 7);      // + 4 u n + c0
         const float* bp = OmT + (size_t)(k0 + (b_ok ? b_row : 0)) * n + 4 * b_kc;
         const size_t pass_stride = 4 * (size_t)n;
         unsigned row_ok = 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) row_ok |= (row_base + lrow0 + 4 * u < m) ? (1u << u) : 0u;
+        for (int u = 0; u < UP; ++u) row_ok |= (row_base + lrow0 + 4 * u < m) ? (1u << u) : 0u;
 
-        auto load_chunk = [&](int it, float (&xv)[8][4], float (&bv)[4]) {
+        auto load_chunk = [&](int it, float (&xv)[UP][4], float (&bv)[4]) {
             const long long c0 = chunk_col(it);
             const float* src0 = xp + c0;
             if (c0 + TC_K <= n) {                               // whole chunk inside the matrix (CTA-uniform)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < UP; ++u) {
                     const float* src = src0 + u * pass_stride;
                     if (!((row_ok >> u) & 1)) {
                         xv[u][0] = 0.f; xv[u][1] = 0.f; xv[u][2] = 0.f; xv[u][3] = 0.f;
@@ -226,7 +225,7 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
             } else {                                            // ragged last chunk
                 const long long col = c0 + 4 * (lane & 7);
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < UP; ++u)
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         xv[u][j] = (((row_ok >> u) & 1) && col + j < n) ? __ldcs(src0 + u * pass_stride + j) : 0.f;
@@ -236,14 +235,14 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
             }
         };
         // one pipeline step: chunk `it` is in (xv, bv); chunk it+2 is loaded into (xl, bl)
-        auto step = [&](int it, float (&xv)[8][4], float (&bv)[4], float (&xl)[8][4], float (&bl)[4]) {
+        auto step = [&](int it, float (&xv)[UP][4], float (&bv)[4], float (&xl)[UP][4], float (&bl)[4]) {
             if (it >= n_my) return;
             if (it + 2 < n_my) load_chunk(it + 2, xl, bl);
             const int s = it % TC_STAGES;
             if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / TC_STAGES - 1) & 1));   // MMAs of chunk it-3 done
             unsigned char* st = smem_raw + (size_t)s * TC_STAGE_BYTES;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < UP; ++u) {
                 const uint32_t lrow = (uint32_t)(lrow0 + 4 * u);
                 const uint32_t off = lrow * 128u + (uint32_t)(((lane & 7) ^ (lrow & 7)) * 16);
                 uint4 hi, lo;
@@ -254,7 +253,7 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
                 *reinterpret_cast<uint4*>(st + off) = hi;
                 *reinterpret_cast<uint4*>(st + TC_A_BYTES + off) = lo;
             }
-            {
+            if (b_thread) {
                 const uint32_t off = (uint32_t)b_row * 128u + (uint32_t)((b_kc ^ (b_row & 7)) * 16);
                 uint4 hi, lo;
                 split_tf32(bv[0], hi.x, lo.x);
@@ -267,7 +266,7 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
             fence_async_smem();
             mbar_arrive(&full_bar[s]);
         };
-        float x0[8][4], x1[8][4], x2[8][4], b0[4], b1[4], b2[4];
+        float x0[UP][4], x1[UP][4], x2[UP][4], b0[4], b1[4], b2[4];
         if (n_my > 0) load_chunk(0, x0, b0);
         if (n_my > 1) load_chunk(1, x1, b1);
 #pragma unroll 1
@@ -279,7 +278,7 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
     } else {
         // ================= MMA issue (warp 8, lane 0) + epilogue (warps 8-11) =================
         constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
-        const int ew = warp - 8;                                             // TMEM lanes 32 ew .. 32 ew + 31
+        const int ew = warp - NPW;                                             // TMEM lanes 32 ew .. 32 ew + 31
         const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
         float acc[2][32];
 #pragma unroll
@@ -288,7 +287,7 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
             for (int c = 0; c < 32; ++c) acc[t][c] = 0.f;
 #pragma unroll 1
         for (int it = 0; it <= n_my; ++it) {
-            if (it < n_my && warp == 8 && lane == 0) {
+            if (it < n_my && warp == NPW && lane == 0) {
                 const int s = it % TC_STAGES;
                 mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
                 tc_fence_after();
@@ -321,10 +320,13 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
                 tc_fence_after();
 #pragma unroll
                 for (int tile = 0; tile < 2; ++tile) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32), v);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) acc[tile][c] += __uint_as_float(v[c]);
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32 + 16 * h), v);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) acc[tile][16 * h + c] += __uint_as_float(v[c]);
+                    }
                 }
                 tc_fence_before();
             }
@@ -344,33 +346,55 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == NPW) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
     }
 }
 
+// ---- A operand from tensor memory (tcgen05.mma "TS" form): lanes = M rows, one 32-bit column per K element ----
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int TS_STAGES = 3;
+constexpr int TS_B_STAGE_BYTES = 2 * TC_B_BYTES;     // Omega / Y chunk, hi + lo (8 KB)
+constexpr int TS_TMEM_COLS = 512;                    // 3 stages x 2 tiles x (32 hi + 32 lo) + 2 buffers x 2 tiles x 32
+constexpr uint32_t TS_D_COL = 384;
+
 // ---------------------------------------------------------------------------------------------------------
-// Bt = Y^T X  (Bt[r][n]).  The output column block (256 columns = two M = 128 tiles) is the MMA's M dimension and
-// the m rows are K:  D[c][k] = sum_i X[i][c] * Y[i][k].  X is row-major, i.e. contiguous along M, so the A operand
-// is staged MN-major (32 consecutive columns of one row per 128-byte line, four rows per 512-byte swizzle atom) --
-// each warp load instruction reads 512 contiguous bytes of a row.  Y (m x r, L2-resident) is staged
-// K-major like Omega above.  A CTA walks down the rows of its column block in 32-row chunks, adds each chunk's TMEM
-// tile into FP32 registers and writes the block out after the last chunk.
-template <bool VEC>
+// Bt = Y^T X with the A operand (X^T tile: M = 256 columns of X, K = 32 rows) written by the producers straight
+// into tensor memory: lane = column, so every warp load reads 128 contiguous bytes of one row of X and no
+// shared-memory staging or transposition of X is needed at all; only the small Y chunk goes through shared memory.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __restrict__ Y, int r, int k0,
+xty_ts_kernel(const float* __restrict__ X, int m, long long n, const float* __restrict__ Y, int r, int k0,
               float* __restrict__ Bt)
 {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+    __shared__ __align__(1024) unsigned char bsm[TS_STAGES * TS_B_STAGE_BYTES];
+    __shared__ __align__(8) uint64_t full_bar[TS_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TS_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ uint32_t tmem_base_sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < TS_STAGES; ++s) {
             mbar_init(&full_bar[s], TC_PRODUCERS);
             mbar_init(&empty_bar[s], 1);
         }
@@ -380,7 +404,7 @@ xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __re
     }
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
-                     "r"(TC_TMEM_COLS));
+                     "r"(TS_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -388,37 +412,30 @@ xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __re
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
 
-    const int nk = (m + 31) / 32;                                           // K chunks per column block
-    const long long nblk = (n + TC_ROWS - 1) / TC_ROWS;                     // column blocks of 256
+    const int nk = (m + 31) / 32;
+    const long long nblk = (n + TC_ROWS - 1) / TC_ROWS;
     const int blk_my = (blockIdx.x < nblk) ? (int)((nblk - 1 - blockIdx.x) / gridDim.x + 1) : 0;
     const int n_my = blk_my * nk;
     auto blk_col = [&](int b) { return ((long long)blockIdx.x + (long long)b * gridDim.x) * TC_ROWS; };
 
     if (warp < 8) {
-        // ================= producers =================
-        // A staging: item = 8 w + u -> row of the chunk item/2, tile item%2; lane -> columns 4 l .. 4 l + 3 of the tile.
-        // B staging: thread t -> output row (k index) t/8, four consecutive rows of the chunk 4 (t%8) ..
+        // ================= producers: lane <-> column (warp w: tile w/4, TMEM lanes 32 (w%4) ..) =================
         const int b_n = tid >> 3, b_kc = tid & 7;
         const bool b_ok = (k0 + b_n < r);
-        auto load_chunk = [&](int it, float (&xv)[8][4], float (&bv)[4]) {
+        const int col_in_blk = (warp >> 2) * 128 + 32 * (warp & 3) + lane;
+        const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
+        const uint32_t a_col = (uint32_t)((warp >> 2) * 64);                // + stage * 128 (+ 32 for lo)
+        auto load_chunk = [&](int it, float (&xv)[32], float (&bv)[4]) {
             const int b = it / nk, kc = it - b * nk;
-            const long long c0 = blk_col(b);
+            const long long col = blk_col(b) + col_in_blk;
             const int i0 = kc * 32;
+            const float* src = X + (size_t)i0 * n + col;
+            if (col < n && i0 + 32 <= m) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int item = warp * 8 + u;
-                const int row = i0 + (item >> 1);
-                const long long col = c0 + (item & 1) * 128 + 4 * lane;
-                const float* src = X + (size_t)row * n + col;
-                if (row >= m || col >= n) {
-                    xv[u][0] = 0.f; xv[u][1] = 0.f; xv[u][2] = 0.f; xv[u][3] = 0.f;
-                } else if (VEC) {                                   // n % 4 == 0: col + 3 < n
-                    const float4 q = GGP_TC_LD(reinterpret_cast<const float4*>(src));
-                    xv[u][0] = q.x; xv[u][1] = q.y; xv[u][2] = q.z; xv[u][3] = q.w;
-                } else {
+                for (int k = 0; k < 32; ++k) xv[k] = GGP_TC_LD(src + (size_t)k * n);
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) xv[u][j] = (col + j < n) ? __ldcs(src + j) : 0.f;
-                }
+                for (int k = 0; k < 32; ++k) xv[k] = (col < n && i0 + k < m) ? GGP_TC_LD(src + (size_t)k * n) : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -426,41 +443,40 @@ xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __re
                 bv[j] = (b_ok && row < m) ? __ldg(Y + (size_t)row * r + k0 + b_n) : 0.f;
             }
         };
-        auto step = [&](int it, float (&xv)[8][4], float (&bv)[4], float (&xl)[8][4], float (&bl)[4]) {
+        auto step = [&](int it, float (&xv)[32], float (&bv)[4], float (&xl)[32], float (&bl)[4]) {
             if (it >= n_my) return;
             if (it + 2 < n_my) load_chunk(it + 2, xl, bl);
-            const int s = it % TC_STAGES;
-            if (it >= TC_STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / TC_STAGES - 1) & 1));
-            unsigned char* st = smem_raw + (size_t)s * TC_STAGE_BYTES;
+            const int s = it % TS_STAGES;
+            if (it >= TS_STAGES) {
+                mbar_wait(&empty_bar[s], (uint32_t)((it / TS_STAGES - 1) & 1));     // MMAs of chunk it-3 have read the stage
+                tc_fence_after();
+            }
+            const uint32_t ta = tmem_base + t_lane + (uint32_t)(s * 128) + a_col;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int item = warp * 8 + u;
-                const uint32_t krow = (uint32_t)(item >> 1);
-                const uint32_t gmb = (uint32_t)((item & 1) * 4 + (lane >> 3));
-                const uint32_t off = gmb * 4096u + (krow >> 2) * 512u + (krow & 3) * 128u +
-                                     (uint32_t)((((lane & 7) >> 1) ^ (krow & 3)) * 32 + (lane & 1) * 16);
-                uint4 hi, lo;
-                split_tf32(xv[u][0], hi.x, lo.x);
-                split_tf32(xv[u][1], hi.y, lo.y);
-                split_tf32(xv[u][2], hi.z, lo.z);
-                split_tf32(xv[u][3], hi.w, lo.w);
-                *reinterpret_cast<uint4*>(st + off) = hi;
-                *reinterpret_cast<uint4*>(st + TC_A_BYTES + off) = lo;
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) split_tf32(xv[16 * h + k], hi[k], lo[k]);
+                tmem_st16(ta + 16 * h, hi);
+                tmem_st16(ta + 32 + 16 * h, lo);
             }
             {
+                unsigned char* st = bsm + (size_t)s * TS_B_STAGE_BYTES;
                 const uint32_t off = (uint32_t)b_n * 128u + (uint32_t)((b_kc ^ (b_n & 7)) * 16);
                 uint4 hi, lo;
                 split_tf32(bv[0], hi.x, lo.x);
                 split_tf32(bv[1], hi.y, lo.y);
                 split_tf32(bv[2], hi.z, lo.z);
                 split_tf32(bv[3], hi.w, lo.w);
-                *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + off) = hi;
-                *reinterpret_cast<uint4*>(st + 2 * TC_A_BYTES + TC_B_BYTES + off) = lo;
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + TC_B_BYTES + off) = lo;
             }
+            tmem_wait_st();
             fence_async_smem();
+            tc_fence_before();
             mbar_arrive(&full_bar[s]);
         };
-        float x0[8][4], x1[8][4], x2[8][4], b0[4], b1[4], b2[4];
+        float x0[32], x1[32], x2[32], b0[4], b1[4], b2[4];
         if (n_my > 0) load_chunk(0, x0, b0);
         if (n_my > 1) load_chunk(1, x1, b1);
 #pragma unroll 1
@@ -471,7 +487,7 @@ xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __re
         }
     } else {
         // ================= MMA issue (warp 8, lane 0) + epilogue (warps 8-11) =================
-        constexpr uint32_t idesc = umma_idesc_tf32(128, 32) | (1u << 15);      // A is MN-major
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
         const int ew = warp - 8;
         const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
         float acc[2][32];
@@ -482,25 +498,22 @@ xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __re
 #pragma unroll 1
         for (int it = 0; it <= n_my; ++it) {
             if (it < n_my && warp == 8 && lane == 0) {
-                const int s = it % TC_STAGES;
-                mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
+                const int s = it % TS_STAGES;
+                mbar_wait(&full_bar[s], (uint32_t)((it / TS_STAGES) & 1));
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE_BYTES);
-                const uint32_t a_lo = a_hi + TC_A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+                const uint32_t b_hi = smem_u32(bsm + (size_t)s * TS_B_STAGE_BYTES);
                 const uint32_t b_lo = b_hi + TC_B_BYTES;
 #pragma unroll
                 for (int tile = 0; tile < 2; ++tile) {
-                    const uint32_t d = tmem_base + (uint32_t)((it & 1) * 64 + tile * 32);
+                    const uint32_t d = tmem_base + TS_D_COL + (uint32_t)((it & 1) * 64 + tile * 32);
+                    const uint32_t a_hi = tmem_base + (uint32_t)(s * 128 + tile * 64);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        const uint64_t ah = umma_desc_mn_sw128_32b(a_hi + tile * 16384 + t * 1024, 4096, 512);
-                        const uint64_t al = umma_desc_mn_sw128_32b(a_lo + tile * 16384 + t * 1024, 4096, 512);
                         const uint64_t bh = umma_desc_sw128(b_hi + t * 32);
                         const uint64_t bl = umma_desc_sw128(b_lo + t * 32);
-                        umma_tf32(d, al, bh, idesc, t > 0 ? 1u : 0u);
-                        umma_tf32(d, ah, bl, idesc, 1u);
-                        umma_tf32(d, ah, bh, idesc, 1u);
+                        umma_tf32_ts(d, a_hi + 32 + 8 * t, bh, idesc, t > 0 ? 1u : 0u);     // x_lo * y_hi
+                        umma_tf32_ts(d, a_hi + 8 * t, bl, idesc, 1u);                        // x_hi * y_lo
+                        umma_tf32_ts(d, a_hi + 8 * t, bh, idesc, 1u);                        // x_hi * y_hi
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -514,13 +527,12 @@ xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __re
 #pragma unroll
                 for (int tile = 0; tile < 2; ++tile) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32), v);
+                    tmem_ld32(tmem_base + t_lane + TS_D_COL + (uint32_t)((j & 1) * 64 + tile * 32), v);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) acc[tile][c] += __uint_as_float(v[c]);
                 }
                 tc_fence_before();
                 if ((j + 1) % nk == 0) {
-                    // last chunk of a column block: write Bt[k0 + c][col] and restart the sums
                     const long long c0 = blk_col(j / nk);
 #pragma unroll
                     for (int tile = 0; tile < 2; ++tile) {
@@ -540,7 +552,7 @@ xty_tc_kernel(const float* __restrict__ X, int m, long long n, const float* __re
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS_TMEM_COLS));
     }
 }
 
@@ -595,11 +607,11 @@ int ggp_rsvd_sketch_tc_f32(const float* X, int m, long long n, const float* Omeg
     if (gx > nchunk) gx = nchunk;
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES;
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-    GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int k0 = 0; k0 < r; k0 += 32) {
-        if (vec) sketch_tc_kernel<true><<<dim3((unsigned)gx, gy), TC_THREADS, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
-        else sketch_tc_kernel<false><<<dim3((unsigned)gx, gy), TC_THREADS, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
+        if (vec) sketch_tc_kernel<true, 8><<<dim3((unsigned)gx, gy), 384, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
+        else sketch_tc_kernel<false, 8><<<dim3((unsigned)gx, gy), 384, smem, st>>>(X, m, n, OmegaT, r, k0, partial);
         GGP_CUDA(cudaGetLastError());
         tc_reduce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(partial, (int)gx, m, r, k0, Y_out);
         GGP_CUDA(cudaGetLastError());
@@ -615,13 +627,8 @@ int ggp_rsvd_xty_tc_f32(const float* X, int m, long long n, const float* Y, int 
     const long long nblk = (n + TC_ROWS - 1) / TC_ROWS;
     long long gx = tc_sm_count();
     if (gx > nblk) gx = nblk;
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES;
-    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-    GGP_CUDA(cudaFuncSetAttribute(xty_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GGP_CUDA(cudaFuncSetAttribute(xty_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int k0 = 0; k0 < r; k0 += 32) {
-        if (vec) xty_tc_kernel<true><<<(unsigned)gx, TC_THREADS, smem, st>>>(X, m, n, Y, r, k0, Bt_out);
-        else xty_tc_kernel<false><<<(unsigned)gx, TC_THREADS, smem, st>>>(X, m, n, Y, r, k0, Bt_out);
+        xty_ts_kernel<<<(unsigned)gx, TC_THREADS, 0, st>>>(X, m, n, Y, r, k0, Bt_out);
         GGP_CUDA(cudaGetLastError());
     }
     return GGP_OK;

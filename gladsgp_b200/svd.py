@@ -1,9 +1,11 @@
 """B200 randomized SVD: drop-in for /root/reference/src/svd.py:12-82 (`randomized_svd`).
 
 Same signature and return shapes; the three products over the (m, n) float32 ensemble
-(src/svd.py:52,56,60) run as streaming CUDA passes (csrc/ggp_rsvd.cu), the m x r QR and the r x r
-eigen-problem run in torch/cuSOLVER on the device.  The Gaussian test matrix is drawn from the global
-np.random stream exactly as the reference does (src/svd.py:51) unless `omega` is injected.
+(src/svd.py:52,56,60) run as streaming passes on the tcgen05 tensor cores (3xTF32 split products with
+FP32-level accuracy, csrc/ggp_rsvd_tc.cu; the FP32-FMA kernels of csrc/ggp_rsvd.cu remain available as
+ops.rsvd_sketch / ops.rsvd_xty), the m x r QR and the r x r eigen-problem run in torch/cuSOLVER on the
+device.  The Gaussian test matrix is drawn from the global np.random stream exactly as the reference does
+(src/svd.py:51) unless `omega` is injected.
 """
 import numpy as np
 
@@ -24,13 +26,13 @@ def randomized_svd(X, p, k=None, q=1, return_error=False, omega=None, return_dev
     if omega is None:
         omega = np.random.normal(size=(n, r)).astype(np.float32)              # svd.py:51
     omT = torch.as_tensor(np.ascontiguousarray(np.asarray(omega, dtype=np.float32).T), device='cuda')
-    ws = torch.empty(_lib.load().ggp_rsvd_workspace_bytes(m), dtype=torch.uint8, device='cuda')
-    Y = ops.rsvd_sketch(Xd, omT, ws)                                          # svd.py:52  Y = X @ omega
+    ws = torch.empty(_lib.load().ggp_rsvd_tc_workspace_bytes(m), dtype=torch.uint8, device='cuda')
+    Y = ops.rsvd_sketch_tc(Xd, omT, ws)                                       # svd.py:52  Y = X @ omega
     for _ in range(q):                                                        # svd.py:55-56  Y = X @ X.T @ Y
-        Zt = ops.rsvd_xty(Xd, Y)                                              #   (X^T Y)^T, (r, n)
-        Y = ops.rsvd_sketch(Xd, Zt, ws)                                       #   X (X^T Y)
+        Zt = ops.rsvd_xty_tc(Xd, Y)                                           #   (X^T Y)^T, (r, n)
+        Y = ops.rsvd_sketch_tc(Xd, Zt, ws)                                    #   X (X^T Y)
     Q, _ = torch.linalg.qr(Y, mode='reduced')                                 # svd.py:59
-    B = ops.rsvd_xty(Xd, Q.contiguous())                                      # svd.py:60  B = Q.T @ X, (r, n)
+    B = ops.rsvd_xty_tc(Xd, Q.contiguous())                                   # svd.py:60  B = Q.T @ X, (r, n)
     # small SVD of B via the r x r Gram matrix in FP64 (svd.py:63)
     Bd = B.double()
     lam, E = torch.linalg.eigh(Bd @ Bd.T)

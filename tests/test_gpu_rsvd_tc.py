@@ -1,0 +1,65 @@
+"""tcgen05 (3xTF32) rSVD passes vs FP64 NumPy and vs the FP32-FMA kernels (src/svd.py:52-60 products)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(128, 64, 8), (256, 4096, 25), (512, 20001, 25), (100, 5003, 25), (700, 9000, 40), (1500, 3001, 25), (33, 257, 3)]
+
+
+@pytest.mark.parametrize('m,n,r', CASES)
+def test_sketch_and_xty_on_tensor_cores(cuda, m, n, r):
+    import torch
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(m * 7 + r)
+    X = (rng.standard_normal((m, n)) * rng.uniform(0.1, 3, size=(1, n))).astype(np.float32)
+    Om = rng.standard_normal((r, n)).astype(np.float32)
+    Yh = rng.standard_normal((m, r)).astype(np.float32)
+    Xd, Od, Yd = (torch.as_tensor(a, device='cuda') for a in (X, Om, Yh))
+    X64 = X.astype(np.float64)
+    ref = X64 @ Om.astype(np.float64).T
+    got = ops.rsvd_sketch_tc(Xd, Od).cpu().numpy()
+    # FP32-level: the split keeps ~21 bits per product and chunk sums are added in round-to-nearest FP32
+    assert np.abs(got - ref).max() <= 1e-6 * np.abs(ref).max()
+    refb = Yh.astype(np.float64).T @ X64
+    gotb = ops.rsvd_xty_tc(Xd, Yd).cpu().numpy()
+    assert gotb.shape == (r, n)
+    assert np.abs(gotb - refb).max() <= 1e-6 * np.abs(refb).max()
+    if m <= 1024:
+        simt = ops.rsvd_sketch(Xd, Od).cpu().numpy()
+        assert np.abs(got - simt).max() <= 2e-6 * np.abs(ref).max()
+    # deterministic: same bits on a second call
+    assert np.array_equal(got, ops.rsvd_sketch_tc(Xd, Od).cpu().numpy())
+    assert np.array_equal(gotb, ops.rsvd_xty_tc(Xd, Yd).cpu().numpy())
+
+
+def test_exact_on_tf32_representable_inputs(cuda):
+    """Inputs that are exactly representable in TF32 with small integer values: every product and sum is exact."""
+    import torch
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(0)
+    m, n, r = 256, 2048, 25
+    X = rng.integers(-8, 9, size=(m, n)).astype(np.float32)
+    Om = rng.integers(-4, 5, size=(r, n)).astype(np.float32)
+    Yh = rng.integers(-4, 5, size=(m, r)).astype(np.float32)
+    Xd, Od, Yd = (torch.as_tensor(a, device='cuda') for a in (X, Om, Yh))
+    assert np.array_equal(ops.rsvd_sketch_tc(Xd, Od).cpu().numpy(), (X.astype(np.int64) @ Om.astype(np.int64).T).astype(np.float32))
+    assert np.array_equal(ops.rsvd_xty_tc(Xd, Yd).cpu().numpy(), (Yh.astype(np.int64).T @ X.astype(np.int64)).astype(np.float32))
+
+
+def test_randomized_svd_large_m(cuda):
+    """m > 1024 (cfg5-sized ensembles) goes through the tensor-core passes; compare with a dense SVD."""
+    from gladsgp_b200 import svd
+    rng = np.random.default_rng(3)
+    m, n, p = 1300, 6000, 12
+    U0, _ = np.linalg.qr(rng.standard_normal((m, p)))
+    V0, _ = np.linalg.qr(rng.standard_normal((n, p)))
+    s0 = np.linspace(50, 5, p)
+    X = ((U0 * s0) @ V0.T + 1e-3 * rng.standard_normal((m, n))).astype(np.float32)
+    np.random.seed(1)
+    U, S, Vh = svd.randomized_svd(X, p, k=8, q=1)
+    s_all = np.linalg.svd(X.astype(np.float64), compute_uv=False)
+    np.testing.assert_allclose(S, s_all[:p], rtol=2e-4)
+    rec = (U * S) @ Vh
+    best = np.sqrt(np.sum(s_all[p:] ** 2))                      # error of the optimal rank-p approximation
+    assert np.linalg.norm(rec - X) <= 1.02 * best
