@@ -43,3 +43,56 @@ def predict_sharded(predictor, xpred):
     lo, hi = shard_bounds(xpred.shape[0], rank, world)
     mean, var = predictor.predict(np.ascontiguousarray(xpred[lo:hi]))
     return all_gather_concat(mean, dim=1), all_gather_concat(var, dim=1)
+
+
+def randomized_svd_sharded(X_slab, p, k=None, q=1, omega_slab=None, products=None):
+    """src/svd.py:12-82 with the ensemble sharded by output-column slab: rank g holds
+    X[:, c0:c1] (m, n_local) on its GPU and streams only that slab.
+
+      Y = sum_g X_g Omega_g              -> all_reduce of an (m, r) matrix            (svd.py:52)
+      Y = sum_g X_g (X_g^T Y)            -> one all_reduce per power iteration        (svd.py:55-56)
+      Q = qr(Y)                          -> replicated (same Y on every rank)         (svd.py:59)
+      B_g = Q^T X_g                      -> stays sharded: it is Vh sharded           (svd.py:60)
+      B B^T = sum_g B_g B_g^T            -> all_reduce of an (r, r) matrix            (svd.py:63)
+
+    Returns (U (m, p), S (p,), Vh_slab (p, n_local)) as tensors on X_slab's device.  `omega_slab` is the block of
+    rows of the (n, r) Gaussian test matrix that belongs to this slab; to reproduce a single-GPU run every rank
+    draws the full matrix from the same seeded np.random stream and slices it (src/svd.py:51 draws it from the
+    global stream).  `products` = (sketch(X, omegaT) -> X @ omegaT.T, xty(X, Y) -> Y.T @ X); default: the
+    tensor-core kernels (ops.rsvd_sketch_tc / ops.rsvd_xty_tc)."""
+    import torch
+    import torch.distributed as dist
+    if k is None:
+        k = p
+    r = p + k
+    if products is None:
+        from . import ops
+        products = (ops.rsvd_sketch_tc, ops.rsvd_xty_tc)
+    sketch, xty = products
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def allsum(t):
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    n_local = X_slab.shape[1]
+    if omega_slab is None:
+        raise ValueError('omega_slab (n_local, r) is required: slice it from the rank-consistent test matrix')
+    omT = torch.as_tensor(np.ascontiguousarray(np.asarray(omega_slab, dtype=np.float32).T), device=X_slab.device)
+    if omT.shape != (r, n_local):
+        raise ValueError('omega_slab must have shape (n_local, p + k)')
+    Y = allsum(sketch(X_slab, omT))
+    for _ in range(q):
+        Zt = xty(X_slab, Y)
+        Y = allsum(sketch(X_slab, Zt.contiguous()))
+    Q, _ = torch.linalg.qr(Y, mode='reduced')
+    B = xty(X_slab, Q.contiguous()).double()                  # (r, n_local)
+    G = allsum(B @ B.T)
+    lam, E = torch.linalg.eigh(G)
+    lam = torch.flip(lam, dims=[0]).clamp_min(0.0)
+    E = torch.flip(E, dims=[1])
+    S = torch.sqrt(lam)
+    U = (Q.double() @ E).float()
+    Vh = ((E.T @ B) / S.clamp_min(1e-300)[:, None]).float()
+    return U[:, :p], S[:p].float(), Vh[:p]

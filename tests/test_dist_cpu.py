@@ -57,3 +57,47 @@ def test_two_rank_gloo_gather():
         np.testing.assert_array_equal(full, np.arange(7) * 10.0)
         np.testing.assert_array_equal(allm, exp_mean)
         assert tmax == 2.0
+
+
+def _svd_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from gladsgp_b200.dist import randomized_svd_sharded
+    rng = np.random.RandomState(11)
+    m, n, p = 40, 501, 6
+    X = (rng.standard_normal((m, 8)) @ rng.standard_normal((8, n)) + 0.01 * rng.standard_normal((m, n))).astype(np.float32)
+    omega = np.random.RandomState(5).normal(size=(n, p)).astype(np.float32)      # same stream on every rank
+    lo, hi = shard_bounds(n, rank, world)
+    products = (lambda A, omT: A @ omT.T, lambda A, Y: Y.T @ A)                   # stand-ins for the CUDA passes
+    U, S, Vh = randomized_svd_sharded(torch.as_tensor(X[:, lo:hi].copy()), p, k=0, q=1, omega_slab=omega[lo:hi],
+                                      products=products)
+    Vh_full = all_gather_concat(Vh, dim=1)
+    q.put((rank, U.numpy(), S.numpy(), Vh_full.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_rsvd_matches_single_process():
+    """rSVD sharded by output-column slab == the oracle on the whole matrix with the same test matrix."""
+    from helpers import svd_oracle
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_svd_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    rng = np.random.RandomState(11)
+    m, n, p = 40, 501, 6
+    X = (rng.standard_normal((m, 8)) @ rng.standard_normal((8, n)) + 0.01 * rng.standard_normal((m, n))).astype(np.float32)
+    omega = np.random.RandomState(5).normal(size=(n, p)).astype(np.float32)
+    U0, S0, Vh0 = svd_oracle.randomized_svd(X, p, k=0, q=1, omega=omega)
+    for rank, U, S, Vh in res:
+        np.testing.assert_allclose(S, S0, rtol=2e-4)
+        np.testing.assert_allclose((U * S) @ Vh, (U0 * S0) @ Vh0, atol=2e-3 * float(S0[0]) / np.sqrt(m))
+    np.testing.assert_array_equal(res[0][1], res[1][1])         # U is replicated
+    np.testing.assert_array_equal(res[0][3], res[1][3])         # gathered Vh identical on both ranks

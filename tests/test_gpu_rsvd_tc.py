@@ -63,3 +63,18 @@ def test_randomized_svd_large_m(cuda):
     rec = (U * S) @ Vh
     best = np.sqrt(np.sum(s_all[p:] ** 2))                      # error of the optimal rank-p approximation
     assert np.linalg.norm(rec - X) <= 1.02 * best
+
+
+def test_sharded_rsvd_single_rank_equals_randomized_svd(cuda):
+    """dist.randomized_svd_sharded on one rank (no process group) == svd.randomized_svd with the same test matrix."""
+    import torch
+    from gladsgp_b200 import svd, dist as gdist
+    rng = np.random.default_rng(8)
+    m, n, p = 96, 4001, 10
+    X = (rng.standard_normal((m, 12)) @ rng.standard_normal((12, n)) + 0.01 * rng.standard_normal((m, n))).astype(np.float32)
+    omega = rng.standard_normal((n, p)).astype(np.float32)
+    U0, S0, Vh0 = svd.randomized_svd(X, p, k=0, q=1, omega=omega)
+    U, S, Vh = gdist.randomized_svd_sharded(torch.as_tensor(X, device='cuda'), p, k=0, q=1, omega_slab=omega)
+    np.testing.assert_array_equal(S.cpu().numpy(), S0)
+    np.testing.assert_array_equal(U.cpu().numpy(), U0)
+    np.testing.assert_array_equal(Vh.cpu().numpy(), Vh0)
