@@ -266,7 +266,7 @@ def run_ours(args):
     data.standardize_y(y_mean=mu, y_sd=sd)
     np.random.seed(1234)
     torch.cuda.synchronize(); t_svd = time.perf_counter()
-    U, S, Vh = svd.randomized_svd(data.sim_data.y_std, 25, k=0, q=1)
+    U, S, Vh = svd.randomized_svd(data.sim_data.y_std_device(), 25, k=0, q=1)   # device-resident since standardize_y
     torch.cuda.synchronize(); svd_s = time.perf_counter() - t_svd
     K = ((S[:PU, None] * Vh[:PU]) / np.sqrt(M)).astype(np.float32)
     data.create_K_basis(K=K)
@@ -318,13 +318,17 @@ def run_ours(args):
 
     # ---------------- end-to-end through the public API with host buffers (`e2e`)
     np.random.seed(4321 + rank)
-    model.do_mcmc_chains(args.warmup, chains)                         # warm the path
+    model.do_mcmc_chains(max(args.warmup, args.steps), chains)        # warm the path (staging buffers at full size)
     barrier()
     t0 = time.perf_counter()
     draws, lps = model.do_mcmc_chains(args.steps, chains)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    if os.environ.get('BENCH_E2E_DEBUG'):
+        for _ in range(5):
+            t0 = time.perf_counter(); model.do_mcmc_chains(args.steps, chains); torch.cuda.synchronize()
+            sys.stderr.write('e2e repeat %.1f ms (first %.1f ms, device pass %.1f ms)\n' % ((time.perf_counter() - t0) * 1e3, e2e_s * 1e3, dev_ms))
     h2d = 2 * P * chains * 8
     d2h = (P + 1) * chains * 8 + 8 * chains / max(args.steps, 1)
 

@@ -104,6 +104,8 @@ class McmcEngine:
         self.set_tables(tables)
         nb = self.lib.ggp_mcmc_workspace_bytes(self.m, self.d, self.pu, self.n_chains)
         self.ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        self._pin = {}
+        self._h2d_done = None
         self.theta = torch.zeros((self.n_chains, self.P), dtype=torch.float64, device=dev)
         self.sigwl = torch.zeros((self.n_chains, self.pu), dtype=torch.float64, device=dev)
         self.upos = torch.zeros(self.n_chains, dtype=torch.int64, device=dev)
@@ -166,7 +168,15 @@ class McmcEngine:
                 uniforms = torch.as_tensor(np.ascontiguousarray(uniforms, dtype=np.float64))
             uniforms = uniforms.reshape(self.n_chains, -1)
             if uniforms.device.type != 'cuda':
-                uniforms = uniforms.pin_memory().to(dev, non_blocking=True)
+                # host -> device through a cached page-locked staging buffer (page-locking per call costs more than
+                # the copy and its cost varies a lot between hosts)
+                if self._h2d_done is not None:
+                    self._h2d_done.synchronize()           # the previous upload has left the staging buffer
+                stage = self._pinned('uniforms', uniforms.numel(), torch.float64)
+                stage.copy_(uniforms.reshape(-1))
+                uniforms = stage.to(dev, non_blocking=True).reshape(self.n_chains, -1)
+                self._h2d_done = torch.cuda.Event()
+                self._h2d_done.record()
             keep.append(uniforms)
             a.uniforms, a.n_uniform = uniforms.data_ptr(), uniforms.shape[1]
             self.upos.zero_()
@@ -191,6 +201,22 @@ class McmcEngine:
         return dict(draws=draws, lp=lp, accepted=acc, consumed=self.upos,
                     kernel_ms=(kms[0], kms[1]) if time_kernels else None,
                     eval_count=cnt.cpu().numpy() if cnt is not None else None)
+
+
+    def _pinned(self, name, numel, dtype):
+        """Cached page-locked host buffer (grown on demand) -> view of `numel` elements."""
+        buf = self._pin.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = self.torch.empty(max(int(numel), 1), dtype=dtype).pin_memory()
+            self._pin[name] = buf
+        return buf[:numel]
+
+    def to_host(self, t, name):
+        """Device tensor -> NumPy copy through a cached page-locked buffer."""
+        stage = self._pinned(name, t.numel(), t.dtype)
+        stage.copy_(t.reshape(-1), non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return stage.numpy().reshape(tuple(t.shape)).copy()
 
 
 class Predictor:

@@ -219,14 +219,14 @@ class SepiaModel:
             st = step if step.ndim == 1 else step[done:done + k]
             out = eng.run(k, st, uniforms=us, do_propMH=do_propMH, init_sigwl=init, record=True,
                           record_accept=record_accept)
-            used = out['consumed'].cpu().numpy()
+            used = eng.to_host(out['consumed'], 'consumed')
             if n_chains == 1:
                 np.random.set_state(state)
                 np.random.random_sample(int(used[0]))
-            draws.append(out['draws'].cpu().numpy())
-            lps.append(out['lp'].cpu().numpy())
+            draws.append(eng.to_host(out['draws'], 'draws'))
+            lps.append(eng.to_host(out['lp'], 'lp'))
             if record_accept:
-                accs.append(out['accepted'].cpu().numpy())
+                accs.append(eng.to_host(out['accepted'], 'accepted'))
             self.launches += (1 if init else 0) + 4 * k
             init = False
             done += k
