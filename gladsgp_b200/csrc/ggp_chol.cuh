@@ -581,26 +581,50 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
 }
 
 // Cluster size for `ntasks` independent matrices: one CTA per matrix when the machine is already full, otherwise
-// the largest power of two (<= 8, the portable cluster limit) that still fits all clusters in one wave of
-// GGP_CTAS_PER_SM resident CTAs per SM.  GGP_CLUSTER=<n> overrides (developer experiments).
-inline int choose_cluster(long long ntasks)
+// the largest power of two that still fits all clusters in one wave of GGP_CTAS_PER_SM resident CTAs per SM: up to 8
+// (the portable cluster limit), 16 for matrices of 1024 rows and more (cfg 5: one chain of 20 PCs at m = 4096 runs
+// 0.80 -> 0.55 s per step).  GGP_CLUSTER=<n> overrides (developer experiments).
+inline int choose_cluster(long long ntasks, int Mp)
 {
     if (const char* e = getenv("GGP_CLUSTER")) {
         int g = atoi(e);
-        if (g == 1 || g == 2 || g == 4 || g == 8) return g;
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16) return g;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long slots = (long long)sms * GGP_CTAS_PER_SM;
+    const int gmax = (Mp >= 1024) ? 16 : 8;
     int g = 1;
-    while (g < 8 && ntasks * (g * 2) <= slots) g *= 2;
+    while (g < gmax && ntasks * (g * 2) <= slots) g *= 2;
     return g;
+}
+
+// a 16-CTA cluster is beyond the portable size: ask the driver whether this kernel / shared-memory size can be
+// co-scheduled that way on this device; otherwise stay at 8
+template <typename K>
+inline int checked_cluster(K kern, int G, size_t smem)
+{
+    if (G <= 8) return G;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 8; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); return 8; }
+    return G;
 }
 
 template <typename K, typename... Args>
 inline cudaError_t launch_maybe_cluster(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, int G, Args... args)
 {
+    if (G > 8) {       // beyond the portable cluster size: opt in (16 CTAs still fit one GPC)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -273,10 +273,11 @@ int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long 
         return GGP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = choose_cluster(B);
+    int G = choose_cluster(B, round_up32(m));
     const long long ls = packed_doubles(Mp);
     if (G > 1) {
         GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        G = checked_cluster(loglik_batched_kernel<true>, G, smem);
         GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
         GGP_CUDA(launch_maybe_cluster(loglik_batched_kernel<true>, dim3(B * G), dim3(NT), smem, st, G, X, m, Mp, d, W, w_stride,
                                       beta, lamz, diag_add, factor_ws, ls, u_out, loglik_out, info_out));

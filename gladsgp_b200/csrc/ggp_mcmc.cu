@@ -291,13 +291,15 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         return GGP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = choose_cluster((long long)a.pu * a.n_chains);
+    int G = choose_cluster((long long)a.pu * a.n_chains, round_up32(a.m));
     const int cpct = eval_carveout_pct(smem);
     if (G > 1) {
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
         GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+        G = checked_cluster(sweep_kernel<true>, G, smem);
+        G = checked_cluster(eval_all_kernel<true>, G, smem);
     } else {
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
