@@ -18,7 +18,7 @@ class GgpError(RuntimeError):
 class McmcArgs(C.Structure):
     _fields_ = [
         ('m', C.c_int), ('d', C.c_int), ('pu', C.c_int), ('n_chains', C.c_int), ('n_steps', C.c_int),
-        ('do_propMH', C.c_int), ('replay', C.c_int), ('init_sigwl', C.c_int),
+        ('do_propMH', C.c_int), ('replay', C.c_int), ('init_sigwl', C.c_int), ('per_chain_data', C.c_int),
         ('X', C.c_void_p), ('W', C.c_void_p), ('lamsim', C.c_void_p),
         ('prior_kind', C.c_void_p), ('prior_a', C.c_void_p), ('prior_b', C.c_void_p),
         ('lo', C.c_void_p), ('hi', C.c_void_p), ('prop_kind', C.c_void_p), ('fixed', C.c_void_p),

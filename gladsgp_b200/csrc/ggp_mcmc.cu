@@ -98,8 +98,22 @@ __global__ void plan_kernel(ggp_mcmc_args a, Plan pl, int t)
     if (a.upos) a.upos[c] = pos;
 }
 
+// per-chain model data (per_chain_data != 0: chain c is its own model on the shared design)
+__device__ __forceinline__ const double* chain_w(const ggp_mcmc_args& a, int c, int j)
+{
+    return a.W + ((size_t)(a.per_chain_data ? c : 0) * a.pu + j) * a.m;
+}
+__device__ __forceinline__ double chain_lamsim(const ggp_mcmc_args& a, int c, int j)
+{
+    return a.lamsim[(size_t)(a.per_chain_data ? c : 0) * a.pu + j];
+}
+__device__ __forceinline__ size_t chain_prior_off(const ggp_mcmc_args& a, int c)
+{
+    return a.per_chain_data ? (size_t)c * ((size_t)a.d * a.pu + 2 * a.pu + 1) : 0;
+}
+
 // parameters of PC j under the current state, optionally with one site replaced by its candidate
-__device__ inline void gather_block_params(const ggp_mcmc_args& a, const double* th, int j, int site, double cand,
+__device__ inline void gather_block_params(const ggp_mcmc_args& a, const double* th, int c, int j, int site, double cand,
                                            double* beta_sm, double& lamz, double& diag_add)
 {
     const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
@@ -111,7 +125,7 @@ __device__ inline void gather_block_params(const ggp_mcmc_args& a, const double*
     lamz = (sz == site) ? cand : th[sz];
     const double lamws = (ss == site) ? cand : th[ss];
     const double lamwos = (so == site) ? cand : th[so];
-    diag_add = 1.0 / (a.lamsim[j] * lamwos) + 1.0 / lamws;
+    diag_add = 1.0 / (chain_lamsim(a, c, j) * lamwos) + 1.0 / lamws;
 }
 
 template <bool CL>
@@ -128,7 +142,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
     double* th = a.theta + (size_t)c * P;
     double* sig = a.sigwl + (size_t)c * pu;
     double* Lp = Lws + ((size_t)c * pu + j) * l_stride;
-    const double* wj = a.W + (size_t)j * a.m;
+    const double* wj = chain_w(a, c, j);
     unsigned char* accd = a.accepted ? a.accepted + ((size_t)t * a.n_chains + c) * P : nullptr;
 
     for (int sl = 0; sl < d + 2; ++sl) {
@@ -142,15 +156,16 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
         const double cand = pl.cand[o];
         double lamz, diag_add;
         __syncthreads();
-        gather_block_params(a, th, j, s, cand, beta_sm, lamz, diag_add);
+        gather_block_params(a, th, c, j, s, cand, beta_sm, lamz, diag_add);
         __syncthreads();
         const double ll_new = eval_block_loglik<CL>(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, nullptr, nullptr);
         if (lead) {
             if (a.eval_count) atomicAdd(a.eval_count, 1ULL);
             const double ll_old = sig[j];
             const double xold = th[s];
-            const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], cand) -
-                                  elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], xold);
+            const size_t po = chain_prior_off(a, c) + s;
+            const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], cand) -
+                                  elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], xold);
             const bool acc = pl.logu[o] < ((ll_new - ll_old) + dprior) + pl.lacorr[o];
             if (acc) {
                 th[s] = cand;
@@ -186,9 +201,9 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
         cand = pl.cand[o];
     }
     double lamz, diag_add;
-    gather_block_params(a, th, j, site, cand, beta_sm, lamz, diag_add);
+    gather_block_params(a, th, c, j, site, cand, beta_sm, lamz, diag_add);
     __syncthreads();
-    const double ll = eval_block_loglik<CL>(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, a.W + (size_t)j * a.m, Lp,
+    const double ll = eval_block_loglik<CL>(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, chain_w(a, c, j), Lp,
                                             nullptr, nullptr);
     if (threadIdx.x == 0 && (!CL || cluster_ctarank() == 0)) {
         if (mode == 0) a.sigwl[(size_t)c * pu + j] = ll;
@@ -214,8 +229,9 @@ __global__ void finalize_kernel(ggp_mcmc_args a, Plan pl, const double* __restri
             so += sig[j];
         }
         const double cand = pl.cand[o];
-        const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], cand) -
-                              elem_log_prior(a.prior_kind[s], a.prior_a[s], a.prior_b[s], th[s]);
+        const size_t po = chain_prior_off(a, c) + s;
+        const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], cand) -
+                              elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], th[s]);
         acc = pl.logu[o] < ((sn - so) + dprior) + pl.lacorr[o];
         if (acc) {
             th[s] = cand;
@@ -231,7 +247,7 @@ __global__ void finalize_kernel(ggp_mcmc_args a, Plan pl, const double* __restri
     for (int blk = 0; blk < 4; ++blk) {
         double sblk = 0.0;
         for (int e = bounds[blk]; e < bounds[blk + 1]; ++e)
-            sblk += elem_log_prior(a.prior_kind[e], a.prior_a[e], a.prior_b[e], th[e]);
+            sblk += elem_log_prior(a.prior_kind[e], a.prior_a[chain_prior_off(a, c) + e], a.prior_b[chain_prior_off(a, c) + e], th[e]);
         lpr += sblk;
     }
     if (a.lp_draws) a.lp_draws[(size_t)t * a.n_chains + c] = ll + lpr;

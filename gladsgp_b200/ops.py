@@ -89,18 +89,28 @@ class McmcEngine:
 
     X (m,d) = zt, W (pu,m) PC weights, lamsim (pu,).  tables: dict of length-P numpy arrays
     (prior_kind, prior_a, prior_b, lo, hi, prop_kind, fixed) in SEPIA sampling order.
+    per_chain=True: chain c is its own model on the shared design -- W (n_chains,pu,m), lamsim (n_chains,pu),
+    tables['prior_a'] / ['prior_b'] (n_chains,P); the other tables are shared.
     """
 
-    def __init__(self, X, W, lamsim, tables, n_chains=1):
+    def __init__(self, X, W, lamsim, tables, n_chains=1, per_chain=False):
         torch = _lib.require_cuda()
         self.torch = torch
         self.lib = _lib.load()
         dev = 'cuda'
+        self.per_chain = bool(per_chain)
         self.X = _f64(X, torch, dev); self.W = _f64(W, torch, dev); self.lamsim = _f64(lamsim, torch, dev)
         self.m, self.d = self.X.shape
-        self.pu = self.W.shape[0]
-        self.P = self.d * self.pu + 2 * self.pu + 1
         self.n_chains = int(n_chains)
+        if self.per_chain:
+            if self.W.dim() != 3 or self.W.shape[0] != self.n_chains or self.W.shape[2] != self.m:
+                raise ValueError('per_chain: W must be (n_chains, pu, m)')
+            self.pu = self.W.shape[1]
+            if tuple(self.lamsim.shape) != (self.n_chains, self.pu):
+                raise ValueError('per_chain: lamsim must be (n_chains, pu)')
+        else:
+            self.pu = self.W.shape[0]
+        self.P = self.d * self.pu + 2 * self.pu + 1
         self.set_tables(tables)
         nb = self.lib.ggp_mcmc_workspace_bytes(self.m, self.d, self.pu, self.n_chains)
         self.ws = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -115,8 +125,9 @@ class McmcEngine:
         torch, dev = self.torch, 'cuda'
         P = self.P
         self.t_prior_kind = torch.as_tensor(np.asarray(tb['prior_kind'], dtype=np.int32).reshape(P), device=dev)
-        self.t_prior_a = _f64(np.asarray(tb['prior_a']).reshape(P), torch, dev)
-        self.t_prior_b = _f64(np.asarray(tb['prior_b']).reshape(P), torch, dev)
+        pshape = (self.n_chains, P) if self.per_chain else (P,)
+        self.t_prior_a = _f64(np.asarray(tb['prior_a']).reshape(pshape), torch, dev)
+        self.t_prior_b = _f64(np.asarray(tb['prior_b']).reshape(pshape), torch, dev)
         self.t_lo = _f64(np.asarray(tb['lo']).reshape(P), torch, dev)
         self.t_hi = _f64(np.asarray(tb['hi']).reshape(P), torch, dev)
         self.t_prop_kind = torch.as_tensor(np.asarray(tb['prop_kind'], dtype=np.int32).reshape(P), device=dev)
@@ -137,12 +148,15 @@ class McmcEngine:
         a = McmcArgs()
         a.m, a.d, a.pu, a.n_chains, a.n_steps = self.m, self.d, self.pu, self.n_chains, int(n_steps)
         a.do_propMH, a.init_sigwl = int(bool(do_propMH)), int(bool(init_sigwl))
+        a.per_chain_data = int(self.per_chain)
         keep = []
         step = _f64(step, torch, dev); keep.append(step)
         if step.dim() == 1:
             a.step_stride_t, a.step_stride_c = 0, 0
         elif step.shape[0] == n_steps and step.dim() == 2:
             a.step_stride_t, a.step_stride_c = self.P, 0
+        elif step.dim() == 3 and step.shape[0] == 1:          # (1, n_chains, P): per-chain sizes, constant in time
+            a.step_stride_t, a.step_stride_c = 0, self.P
         elif step.dim() == 3:
             a.step_stride_t, a.step_stride_c = self.n_chains * self.P, self.P
         else:

@@ -81,6 +81,9 @@ int ggp_factor_unpack_f64(const double* factor_ws, int m, int B, double* L_dense
 typedef struct ggp_mcmc_args {
     int m, d, pu, n_chains, n_steps;
     int do_propMH, replay, init_sigwl;
+    int per_chain_data;    /* 0: every chain samples the same model.  1: chain c is its own model on the shared design X
+                              (e.g. the per-threshold scalar models of fit_scalar_models.py:457-473 fitted together):
+                              W is [n_chains][pu][m], lamsim [n_chains][pu], prior_a / prior_b [n_chains][P] */
     const double* X;       /* [m][d]   zt = [dummy x | t]           */
     const double* W;       /* [pu][m]  PC weights                   */
     const double* lamsim;  /* [pu]     diag(K K^T)                  */

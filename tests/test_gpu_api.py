@@ -233,3 +233,62 @@ def test_reference_workflow_end_to_end(cuda, tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith('test RMSE')][0]
     rmse = float(line.split()[2]); cover = float(line.split()[-1])
     assert rmse < 0.2 and 0.6 < cover <= 1.0, line
+
+
+def test_model_batch_equals_models_fitted_one_by_one(cuda):
+    """gladsgp_b200.batch.ModelBatch (the per-threshold scalar models of fit_scalar_models.py
+    fitted together): every model reaches exactly the state it reaches alone with its own seeded stream."""
+    import copy
+    import io
+    from contextlib import redirect_stdout
+    from sepia.SepiaData import SepiaData
+    from sepia.SepiaModel import SepiaModel
+    from gladsgp_b200.batch import ModelBatch
+    rng = np.random.default_rng(4)
+    m, q = 48, 3
+    t = synthetic.design(m, q, seed=9)
+    ys = [np.sin(3 * t[:, 0]) + 0.1 * rng.standard_normal(m), t[:, 1] ** 2 - t[:, 2] + 0.05 * rng.standard_normal(m),
+          np.cos(2 * t[:, 2]) * t[:, 0] + 0.2 * rng.standard_normal(m)]
+
+    def make(y):
+        d = SepiaData(t_sim=t, y_sim=y.astype(np.float32))
+        d.transform_xt()
+        d.standardize_y()
+        return SepiaModel(d)
+
+    seeds = [11, 22, 33]
+    solo = [make(y) for y in ys]
+    with redirect_stdout(io.StringIO()):
+        for mm, s in zip(solo, seeds):
+            np.random.seed(s)
+            mm.tune_step_sizes(4, 3, prog=False)
+            mm.do_mcmc(6, prog=False)
+    together = [make(y) for y in ys]
+    batch = ModelBatch(together, seeds=seeds)
+    batch.tune_step_sizes(4, 3)
+    batch.do_mcmc(6)
+    for a, b in zip(solo, together):
+        sa, sb = a.get_samples(), b.get_samples()
+        for k in ('betaU', 'lamUz', 'lamWs', 'lamWOs', 'logPost'):
+            np.testing.assert_allclose(sb[k], sa[k], rtol=1e-12, atol=0)
+        for pa, pb in zip(a.params.mcmcList, b.params.mcmcList):
+            np.testing.assert_allclose(pb.mcmc.stepParam, pa.mcmc.stepParam, rtol=1e-12)
+            np.testing.assert_allclose(pb.val, pa.val, rtol=1e-12)
+    # a multivariate batch: two ensembles on one design (own K, own lamWOs prior each)
+    pr1 = make_problem(m=40, q=3, pu=2, seed=5)
+    pr2 = make_problem(m=40, q=3, pu=2, seed=5)
+    pr2['y'] = (pr2['y'] * 1.3 + 0.05 * np.random.default_rng(1).standard_normal(pr2['y'].shape)).astype(pr2['y'].dtype)
+    solo, together = [], []
+    for pr in (pr1, pr2):
+        for lst in (solo, together):
+            d = SepiaData(t_sim=pr['t'], y_sim=pr['y'], y_ind_sim=np.linspace(0, 1, pr['y'].shape[1]))
+            d.transform_xt(); d.standardize_y(); d.create_K_basis(n_pc=2)
+            lst.append(SepiaModel(d))
+    for mm, s in zip(solo, (5, 6)):
+        np.random.seed(s)
+        mm.do_mcmc(5, prog=False)
+    ModelBatch(together, seeds=(5, 6)).do_mcmc(5)
+    for a, b in zip(solo, together):
+        sa, sb = a.get_samples(), b.get_samples()
+        for k in ('betaU', 'lamUz', 'lamWs', 'lamWOs', 'logPost'):
+            np.testing.assert_allclose(sb[k], sa[k], rtol=1e-12, atol=0)
