@@ -68,22 +68,29 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // K-major, 128-byte swizzle: a row is 128 contiguous bytes (32 tf32 = one K chunk), rows 128 B apart, 8-row groups
 // 1024 B apart, and the 16-byte piece kc of row r sits at position kc ^ (r % 8) (Swizzle<3,4,3>; tile 1024-B aligned).
 // A K = 8 step advances the start address by 32 bytes.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+// The same descriptor as two words, so that the issuing thread only adds a byte offset to the low word per MMA
+// (it is a single thread: every instruction it spends on descriptors is on the critical path of the chunk).
+constexpr uint32_t UMMA_SW128_HI = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_sw128_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_join(uint32_t lo, uint32_t hi)
 {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
@@ -102,23 +109,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// issue all tcgen05.ld of an epilogue first, then wait once
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // x = hi + lo with hi on the TF32 grid (round to nearest, ties away -- what cvt.rna.tf32.f32 does, but on the integer
 // pipe: the conversion instruction runs on the quarter-rate XU pipe and was the producers' bottleneck) and lo = x - hi
 // exact in FP32 (|lo| <= 2^-11 |x|); the tensor core reads the upper 19 bits of lo (error <= 2^-21 |x|).
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo)
 {
     hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
@@ -280,6 +277,7 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
         constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
         const int ew = warp - NPW;                                             // TMEM lanes 32 ew .. 32 ew + 31
         const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
+        const uint32_t desc_lo0 = umma_sw128_lo(smem_u32(smem_raw));
         float acc[2][32];
 #pragma unroll
         for (int t = 0; t < 2; ++t)
@@ -291,22 +289,22 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
                 const int s = it % TC_STAGES;
                 mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE_BYTES);
-                const uint32_t a_lo = a_hi + TC_A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
-                const uint32_t b_lo = b_hi + TC_B_BYTES;
+                // descriptor low words: base + (byte offset >> 4); A tile t-step: + 2, next M tile: + 1024, lo: + 2048
+                const uint32_t a_lo0 = desc_lo0 + (uint32_t)s * (TC_STAGE_BYTES >> 4);
+                const uint32_t b_lo0 = a_lo0 + ((2 * TC_A_BYTES) >> 4);
+                const uint32_t d0 = tmem_base + (uint32_t)((it & 1) * 64);
 #pragma unroll
-                for (int tile = 0; tile < 2; ++tile) {
-                    const uint32_t d = tmem_base + (uint32_t)((it & 1) * 64 + tile * 32);
+                for (int t = 0; t < 4; ++t) {
+                    const uint64_t bh = umma_join(b_lo0 + 2 * t, UMMA_SW128_HI);
+                    const uint64_t bl = umma_join(b_lo0 + (TC_B_BYTES >> 4) + 2 * t, UMMA_SW128_HI);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint64_t ah = umma_desc_sw128(a_hi + tile * 16384 + t * 32);
-                        const uint64_t al = umma_desc_sw128(a_lo + tile * 16384 + t * 32);
-                        const uint64_t bh = umma_desc_sw128(b_hi + t * 32);
-                        const uint64_t bl = umma_desc_sw128(b_lo + t * 32);
-                        umma_tf32(d, al, bh, idesc, t > 0 ? 1u : 0u);      // small terms first
-                        umma_tf32(d, ah, bl, idesc, 1u);
-                        umma_tf32(d, ah, bh, idesc, 1u);
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const uint64_t ah = umma_join(a_lo0 + tile * 1024 + 2 * t, UMMA_SW128_HI);
+                        const uint64_t al = umma_join(a_lo0 + (TC_A_BYTES >> 4) + tile * 1024 + 2 * t, UMMA_SW128_HI);
+                        const uint32_t d = d0 + tile * 32;
+                        if (t == 0) umma_tf32<false>(d, al, bh, idesc); else umma_tf32<true>(d, al, bh, idesc);   // small terms first
+                        umma_tf32<true>(d, ah, bl, idesc);
+                        umma_tf32<true>(d, ah, bh, idesc);
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -318,16 +316,14 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
                 const int j = it - 1;
                 mbar_wait(&tmem_full_bar[j & 1], (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64), v0);
+                tmem_ld32(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + 32), v1);
+                tmem_ld_wait();
 #pragma unroll
-                for (int tile = 0; tile < 2; ++tile) {
+                for (int c = 0; c < 32; ++c) acc[0][c] += __uint_as_float(v0[c]);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + t_lane + (uint32_t)((j & 1) * 64 + tile * 32 + 16 * h), v);
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) acc[tile][16 * h + c] += __uint_as_float(v[c]);
-                    }
-                }
+                for (int c = 0; c < 32; ++c) acc[1][c] += __uint_as_float(v1[c]);
                 tc_fence_before();
             }
             // all four epilogue warps are done with TMEM buffer (it-1)&1 before the MMAs of chunk it+1 overwrite it
@@ -353,13 +349,14 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
 }
 
 // ---- A operand from tensor memory (tcgen05.mma "TS" form): lanes = M rows, one 32-bit column per K element ----
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
@@ -490,6 +487,7 @@ xty_ts_kernel(const float* __restrict__ X, int m, long long n, const float* __re
         constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
         const int ew = warp - 8;
         const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
+        const uint32_t desc_lo0 = umma_sw128_lo(smem_u32(bsm));
         float acc[2][32];
 #pragma unroll
         for (int t = 0; t < 2; ++t)
@@ -501,19 +499,19 @@ xty_ts_kernel(const float* __restrict__ X, int m, long long n, const float* __re
                 const int s = it % TS_STAGES;
                 mbar_wait(&full_bar[s], (uint32_t)((it / TS_STAGES) & 1));
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(bsm + (size_t)s * TS_B_STAGE_BYTES);
-                const uint32_t b_lo = b_hi + TC_B_BYTES;
+                const uint32_t b_lo0 = desc_lo0 + (uint32_t)s * (TS_B_STAGE_BYTES >> 4);
+                const uint32_t d0 = tmem_base + TS_D_COL + (uint32_t)((it & 1) * 64);
+                const uint32_t a0 = tmem_base + (uint32_t)(s * 128);
 #pragma unroll
-                for (int tile = 0; tile < 2; ++tile) {
-                    const uint32_t d = tmem_base + TS_D_COL + (uint32_t)((it & 1) * 64 + tile * 32);
-                    const uint32_t a_hi = tmem_base + (uint32_t)(s * 128 + tile * 64);
+                for (int t = 0; t < 4; ++t) {
+                    const uint64_t bh = umma_join(b_lo0 + 2 * t, UMMA_SW128_HI);
+                    const uint64_t bl = umma_join(b_lo0 + (TC_B_BYTES >> 4) + 2 * t, UMMA_SW128_HI);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint64_t bh = umma_desc_sw128(b_hi + t * 32);
-                        const uint64_t bl = umma_desc_sw128(b_lo + t * 32);
-                        umma_tf32_ts(d, a_hi + 32 + 8 * t, bh, idesc, t > 0 ? 1u : 0u);     // x_lo * y_hi
-                        umma_tf32_ts(d, a_hi + 8 * t, bl, idesc, 1u);                        // x_hi * y_lo
-                        umma_tf32_ts(d, a_hi + 8 * t, bh, idesc, 1u);                        // x_hi * y_hi
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const uint32_t d = d0 + tile * 32, a_hi = a0 + tile * 64 + 8 * t;
+                        if (t == 0) umma_tf32_ts<false>(d, a_hi + 32, bh, idesc); else umma_tf32_ts<true>(d, a_hi + 32, bh, idesc);   // x_lo * y_hi
+                        umma_tf32_ts<true>(d, a_hi, bl, idesc);                                    // x_hi * y_lo
+                        umma_tf32_ts<true>(d, a_hi, bh, idesc);                                    // x_hi * y_hi
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -524,13 +522,14 @@ xty_ts_kernel(const float* __restrict__ X, int m, long long n, const float* __re
                 const int j = it - 1;
                 mbar_wait(&tmem_full_bar[j & 1], (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tmem_base + t_lane + TS_D_COL + (uint32_t)((j & 1) * 64), v0);
+                tmem_ld32(tmem_base + t_lane + TS_D_COL + (uint32_t)((j & 1) * 64 + 32), v1);
+                tmem_ld_wait();
 #pragma unroll
-                for (int tile = 0; tile < 2; ++tile) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + t_lane + TS_D_COL + (uint32_t)((j & 1) * 64 + tile * 32), v);
+                for (int c = 0; c < 32; ++c) acc[0][c] += __uint_as_float(v0[c]);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) acc[tile][c] += __uint_as_float(v[c]);
-                }
+                for (int c = 0; c < 32; ++c) acc[1][c] += __uint_as_float(v1[c]);
                 tc_fence_before();
                 if ((j + 1) % nk == 0) {
                     const long long c0 = blk_col(j / nk);

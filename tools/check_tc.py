@@ -59,6 +59,8 @@ def main():
         t_tc = ev(lambda: ops.rsvd_xty_tc(Xd, Yd))
         t_simt = ev(lambda: ops.rsvd_xty(Xd, Yd))
         res['xty_time_ms'] = dict(tc=t_tc, simt=t_simt, tc_gbs=4.0 * m * n / t_tc / 1e6, simt_gbs=4.0 * m * n / t_simt / 1e6)
+    if 'time_ms' in res:
+        print('TIMES sketch tc %.3f ms simt %.3f | xty tc %.3f ms simt %.3f' % (res['time_ms']['tc'], res['time_ms']['simt'], res['xty_time_ms']['tc'], res['xty_time_ms']['simt']))
     print(json.dumps(res))
 
 

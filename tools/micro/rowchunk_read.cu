@@ -100,6 +100,14 @@ __global__ void __launch_bounds__(288) bulk_kernel(const float* __restrict__ X, 
     if (acc == 123.456f) out[0] = acc;
 }
 
+__global__ void fill_kernel(float* X, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        X[i] = (float)(h & 0xFFFFFF) * (1.0f / 16777216.0f) - 0.5f;
+    }
+}
+
 int main(int argc, char** argv)
 {
     const int m = 512;
@@ -107,6 +115,8 @@ int main(int argc, char** argv)
     float* X; float* out;
     cudaMalloc(&X, (size_t)m * n * 4); cudaMalloc(&out, 4);
     cudaMemset(X, 0, (size_t)m * n * 4);
+    if (argc > 1) fill_kernel<<<4096, 256>>>(X, (size_t)m * n);      // pseudo-random contents instead of zeros
+    cudaDeviceSynchronize();
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto time = [&](const char* name, auto launch) {
         launch(); cudaDeviceSynchronize();
