@@ -28,7 +28,7 @@ P = D * PU + 2 * PU + 1
 EVALS_PER_STEP = PU * (D + 4)
 METRIC = 'mcmc_steps_per_s'
 UNIT = 'chain-steps/s'
-SWEEP_DRAM_BYTES_PER_EVAL = 44.35e9 / 6490.0      # ncu, profiles/r1_sweep_kernel_summary.txt
+SWEEP_DRAM_BYTES_PER_EVAL = 45.95e9 / 6490.0      # ncu, profiles/r1b_sweep_kernel_summary.txt
 WORKLOAD = 'cfg3 multivariate PCA emulator: m=512 sims, q=8 params (d=9), pu=10 PCs, SEPIA Metropolis-within-Gibbs'
 
 
@@ -377,7 +377,7 @@ def run_ours(args):
                          'peak_source': 'cuBLAS FP64 GEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)',
                          'traffic': SWEEP_DRAM_BYTES_PER_EVAL * sweep_evals / args.steps,
                          'traffic_source': 'dram__bytes_read+write of one ncu --set full capture of ggp::sweep_kernel '
-                                           '(profiles/r1_sweep_kernel_summary.txt: 44.35 GB / 6490 evaluations), scaled to '
+                                           '(profiles/r1b_sweep_kernel_summary.txt: 45.95 GB / 6490 evaluations), scaled to '
                                            'the evaluations of one launch of this run',
                          'evals_in_timed_launches': sweep_evals, 'kernel_ms_total': sweep_ms,
                          'kernel_share_of_step': sweep_ms / dev_ms, 'lamWOs_wave_ms_total': wos_ms, 'flop_per_eval': flop_eval},

@@ -30,6 +30,15 @@ namespace ggp {
 // optional phase timing (developer diagnostics): cycles spent by warp 0 and warp 7 of block 0 in each phase
 #ifdef GGP_PHASES
 __device__ unsigned long long g_phase[32];
+__device__ unsigned long long g_phase2[128];     // look-ahead variant: [warp][16] cycles per activity, block 0
+#define LA_TICK(slot)                                                                       \
+    do {                                                                                    \
+        if (blockIdx.x == 0 && blockIdx.y == 0) {                                           \
+            unsigned long long now__ = clock64();                                           \
+            if ((threadIdx.x & 31) == 0) g_phase2[(threadIdx.x >> 5) * 16 + (slot)] += now__ - tla__; \
+            tla__ = now__;                                                                  \
+        }                                                                                   \
+    } while (0)
 #define GGP_TICK(slot)                                                                      \
     do {                                                                                    \
         if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 7)) {  \
@@ -49,8 +58,13 @@ __device__ unsigned long long g_phase[32];
     } while (0)
 #else
 #define GGP_TICK(slot) do { } while (0)
+#define LA_TICK(slot) do { } while (0)
 #define GGP_TICKW(w, slot, dep) do { } while (0)
 #endif
+
+// DMMA steps / shared-memory doubles of the covariance distance product (see pair_cov)
+__host__ __device__ inline int cov_ksteps(int d) { return (d + 5) >> 2; }
+__host__ __device__ inline int sc_doubles(int d) { return 128 * cov_ksteps(d); }
 
 struct EvalSmem {
     double* D;      // [32][D_LD]   diagonal block: P on entry, rows of Ljj after the factorisation
@@ -62,18 +76,19 @@ struct EvalSmem {
     double* etab;   // [32] 2^(j/32)
     double* wres;   // [Mp]
     double* sb;     // [d]     sqrt(beta)
-    double* SC;     // [d][32] sqrt(beta)-scaled coordinates of the current panel's columns
+    double* SC;     // [sc_doubles(d)] B fragments of the distance product for the current panel's columns
     int* flag;      // [4]
     int* soff;      // [4*nP] offset (doubles) of sub-slab s = 4*kb + ks such that soff[s] + r*8 + c addresses row r
 };
 
 __host__ __device__ inline size_t eval_smem_bytes(int Mp, int d) {
-    return (size_t)(32 * D_LD + 32 * LT_LD + 32 * MI_LD + 32 + 32 + 8 + 32 + Mp + (size_t)33 * ((d + 1) & ~1)) * sizeof(double) + 16 + (size_t)(Mp / 8) * sizeof(int);
+    return (size_t)(32 * D_LD + 32 * LT_LD + 32 * MI_LD + 32 + 32 + 8 + 32 + Mp + (size_t)sc_doubles(d) + ((d + 1) & ~1)) * sizeof(double) + 16 + (size_t)(Mp / 8) * sizeof(int);
 }
 
 // shared-memory carve-out (percent of 228 KB) that just fits three CTAs: the rest stays L1 so that the
 // B-operand rows of a panel, shared by the eight warps, are served from L1 instead of L2
 inline int eval_carveout_pct(size_t smem) {
+    if (const char* e = getenv("GGP_CARVEOUT_PCT")) return atoi(e);      // developer experiments
     size_t need = GGP_CTAS_PER_SM * (smem + 1024);
     int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
     return pct > 100 ? 100 : pct;
@@ -90,7 +105,7 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     s.red = p;      p += 8;
     s.etab = p;     p += 32;
     s.wres = p;     p += Mp;
-    s.SC = p;       p += (size_t)32 * ((d + 1) & ~1);
+    s.SC = p;       p += (size_t)sc_doubles(d);
     s.sb = p;       p += ((d + 1) & ~1);
     s.flag = reinterpret_cast<int*>(p);
     s.soff = s.flag + 4;
@@ -144,13 +159,22 @@ __device__ inline void fill_slab_offsets(int* soff, int Mp)
 // Latency: the A fragment of the next sub-slab is loaded one iteration ahead into registers; further
 // ahead, lanes 0..4NU-1 pull the A lines of sub-slab s+6 into L2 and lanes 16..31 the B lines of
 // sub-slab s+2 into L1 (the B rows are shared by all warps of the CTA).
+#ifndef GGP_RA
+#define GGP_RA 2          // register ring depth of the A fragments (sub-slabs): loads run GGP_RA - 1 iterations ahead
+#endif
+#ifndef GGP_RB
+#define GGP_RB 2          // same for the B fragments
+#endif
 template <int NU>
 static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const double* __restrict__ Ap,
                                                   const double* __restrict__ Lb, const int* __restrict__ soff, int j,
                                                   int row0, const int (&rb)[2], int g, int q, int a_ld)
 {
     constexpr int PD = 2;                    // prefetch distance in k-blocks (4 sub-slabs each)
+    constexpr int RA = GGP_RA, RB = GGP_RB;
+    static_assert(4 % RA == 0 && 4 % RB == 0, "ring depths must divide the 4 sub-slabs of a k-block");
     const int lane = 4 * g + q;
+    const int nsub = 4 * j;
     // sub-slab pointers: packed factor -> soff table; V workspace (a_ld != 0) -> s * a_ld * 8
     auto a_slab = [&](int s) -> const double* { return a_ld ? Ap + (size_t)s * a_ld * 8 : Ap + soff[s]; };
     // prefetch roles, one 128-byte line per lane and sub-slab group:
@@ -161,15 +185,25 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
     const int pa_off = rb[pa_unit] * 8 + (lane & 3) * 16;
     const int pb_ks = lane >> 3;                                      // 8 lanes per sub-slab, 2 lines each
     const int pb_off = (row0 + 4 * (lane & 7)) * 8;
-    double2 an[NU], bn[4];
-    {
-        const double* sl = a_slab(0);
+    int aoff[NU];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) an[i] = ldcg2(sl + (rb[i] + g) * 8 + 2 * q);
-        const double* sb0 = Lb + soff[0];
+    for (int i = 0; i < NU; ++i) aoff[i] = (rb[i] + g) * 8 + 2 * q;
+    const int boff = (row0 + g) * 8 + 2 * q;
+    double2 ar[RA][NU], br[RB][4];          // fragment rings: slot s % R holds sub-slab s
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) bn[cb] = *reinterpret_cast<const double2*>(sb0 + (row0 + 8 * cb + g) * 8 + 2 * q);
-    }
+    for (int t = 0; t < RA - 1; ++t)
+        if (t < nsub) {
+            const double* sl = a_slab(t);
+#pragma unroll
+            for (int i = 0; i < NU; ++i) ar[t][i] = ldcg2(sl + aoff[i]);
+        }
+#pragma unroll
+    for (int t = 0; t < RB - 1; ++t)
+        if (t < nsub) {
+            const double* sl = Lb + soff[t] + boff;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) br[t][cb] = *reinterpret_cast<const double2*>(sl + 64 * cb);
+        }
     for (int kb = 0; kb < j; ++kb) {
         if (kb + PD < j) {
             const int sp = 4 * (kb + PD);
@@ -181,20 +215,19 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const int s = 4 * kb + ks;
-            double2 a[NU], b[4];
+            // loads of sub-slab s + R - 1 go into the slot that sub-slab s - 1 has just left
+            if (s + RA - 1 < nsub) {
+                const double* sn = a_slab(s + RA - 1);
 #pragma unroll
-            for (int i = 0; i < NU; ++i) a[i] = an[i];
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) b[cb] = bn[cb];
-            if (ks < 3 || kb + 1 < j) {
-                const double* sn = a_slab(s + 1);
-#pragma unroll
-                for (int i = 0; i < NU; ++i) an[i] = ldcg2(sn + (rb[i] + g) * 8 + 2 * q);
-                const double* sbn = Lb + soff[s + 1];
-#pragma unroll
-                for (int cb = 0; cb < 4; ++cb)
-                    bn[cb] = *reinterpret_cast<const double2*>(sbn + (row0 + 8 * cb + g) * 8 + 2 * q);
+                for (int i = 0; i < NU; ++i) ar[(ks + RA - 1) % RA][i] = ldcg2(sn + aoff[i]);
             }
+            if (s + RB - 1 < nsub) {
+                const double* sbn = Lb + soff[s + RB - 1] + boff;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) br[(ks + RB - 1) % RB][cb] = *reinterpret_cast<const double2*>(sbn + 64 * cb);
+            }
+            const double2 (&a)[NU] = ar[ks % RA];
+            const double2 (&b)[4] = br[ks % RB];
             // all even-k DMMAs first, then the odd-k ones: dependent DMMAs on one accumulator are 4*NU apart
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
@@ -225,57 +258,131 @@ static __device__ __forceinline__ void unit_trsm(const double (&p)[4][2], double
 }
 
 // Covariance entries of NU units (8 rows x 32 panel columns each) in the accumulator layout: p = C - p.
-// Row coordinates come from global memory (Xr[r][d], L1/L2 resident) and are scaled by sqrt(beta) on the
-// fly -- the same expression that fills SC, so the two sides round identically; column coordinates of the
-// panel sit in shared memory (SC[k][32]) and are shared by the NU units.  self: rows are training points
-// (diagonal / padding rules).  The 8*NU exponentials go through a per-warp shared-memory scratch
-// (scr[16][32]) and a 4-way unrolled loop, so the exp code exists 4 times in the kernel instead of 32: the
-// fully inlined version made the kernel > 100 KB of SASS and instruction-fetch bound (profiles/README.md).
+// The squared distances are a rank-(d+2) product on the FP64 tensor cores:
+//   -dist(i, c) = [x~_i, |x~_i|^2, 1] . [2 x~_c, -1, -|x~_c|^2],   x~ = sqrt(beta) o x,
+// KS = ceil((d+2)/4) DMMA.8x8x4 steps per 8x8 tile instead of 2d DADD/DFMA per entry (the difference form kept the
+// FP64 pipe -- shared with DMMA -- busy with 16x more instructions; profiles/README.md).  The cancellation costs
+// a few ulp of |x~|^2 in dist, i.e. ~1e-15 relative in a covariance entry for coordinates in [0, 1].
+// Row coordinates come from global memory (Xr[r][d], L1/L2 resident); the panel side (B fragments, shared by all
+// units of a panel) sits in shared memory, filled by fill_panel_coords: SCB[s][cb][lane] = B[k = 4s + lane%4][n = 8cb + lane/4].
+// self: rows are training points (diagonal / padding rules).  The 8*NU exponentials go through a per-warp
+// shared-memory scratch (scr[16][32]) and a 4-way unrolled loop, so the exp code exists 4 times in the kernel
+// instead of 32: the fully inlined version made the kernel > 100 KB of SASS and instruction-fetch bound.
+
+// -dist for NU units x 32 panel columns: dn += [x~, |x~|^2, 1] . B.  KS > 0: compile-time step count (the row values
+// stay in registers: every global load of the pair is in flight before the first use); KS = 0: runtime loop.
+template <int NU, int KS>
+static __device__ __forceinline__ void cov_dist(double (&dn)[2][4][2], const double* const (&xr)[2],
+                                                const double* __restrict__ SCB, const double* __restrict__ sb,
+                                                int d, int q, int lane)
+{
+    if constexpr (KS > 0) {
+        double x[NU][KS];
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+            for (int s = 0; s < KS; ++s) x[i][s] = (4 * s + q < d) ? __ldg(xr[i] + 4 * s + q) : 0.0;
+        double rn[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            double part = 0.0;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                const int k = 4 * s + q;
+                x[i][s] = (k < d) ? x[i][s] * sb[k] : 0.0;
+                part = fma(x[i][s], x[i][s], part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            rn[i] = part;
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int k = 4 * s + q;
+            double a[NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) a[i] = (k < d) ? x[i][s] : ((k == d) ? rn[i] : ((k == d + 1) ? 1.0 : 0.0));
+            const double* bs = SCB + s * 128 + lane;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const double b = bs[cb * 32];
+#pragma unroll
+                for (int i = 0; i < NU; ++i) dmma884(dn[i][cb][0], dn[i][cb][1], a[i], b);
+            }
+        }
+    } else {
+        const int ks = cov_ksteps(d);
+        double rn[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            // squared norm of the scaled row: the four lanes of a row (q = 0..3) each sum the k = q (mod 4) terms
+            double part = 0.0;
+            for (int s = 0; s < ks; ++s) {
+                const int k = 4 * s + q;
+                const double x = (k < d) ? __ldg(xr[i] + k) * sb[k] : 0.0;
+                part = fma(x, x, part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            rn[i] = part;
+        }
+#pragma unroll 1
+        for (int s = 0; s < ks; ++s) {
+            const int k = 4 * s + q;
+            double a[NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const double x = (k < d) ? __ldg(xr[i] + k) * sb[k] : 0.0;
+                a[i] = (k < d) ? x : ((k == d) ? rn[i] : ((k == d + 1) ? 1.0 : 0.0));
+            }
+            const double* bs = SCB + s * 128 + lane;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const double b = bs[cb * 32];
+#pragma unroll
+                for (int i = 0; i < NU; ++i) dmma884(dn[i][cb][0], dn[i][cb][1], a[i], b);
+            }
+        }
+    }
+}
+
 template <int NU>
 static __device__ __forceinline__ void pair_cov(double (&p)[2][4][2], const double* __restrict__ Xr, const int (&r)[2],
-                                                const bool (&row_ok)[2], const double* __restrict__ SC,
+                                                const bool (&row_ok)[2], const double* __restrict__ SCB,
                                                 const double* __restrict__ sb, int d, int m, int row0, int q,
                                                 double inv_lamz, double diag, bool self,
                                                 const double* __restrict__ etab, double* __restrict__ scr, int lane)
 {
-    double dist[NU][4][2];
-    const double* xr[NU];
-    double xnext[NU];
+    double dn[2][4][2];
+    const double* xr[2];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) {
+    for (int i = 0; i < 2; ++i) {
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) { dist[i][cb][0] = 0.0; dist[i][cb][1] = 0.0; }
-        xr[i] = Xr + (size_t)(row_ok[i] ? r[i] : 0) * d;
-        xnext[i] = __ldg(xr[i]);
+        for (int cb = 0; cb < 4; ++cb) { dn[i][cb][0] = 0.0; dn[i][cb][1] = 0.0; }
+        xr[i] = Xr + (size_t)((i < NU && row_ok[i]) ? r[i] : 0) * d;
     }
-    for (int k = 0; k < d; ++k) {
-        double sr[NU];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            sr[i] = xnext[i] * sb[k];
-            if (k + 1 < d) xnext[i] = __ldg(xr[i] + k + 1);
-        }
-        const double* sc = SC + k * 32 + 2 * q;
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-            const double2 c2 = *reinterpret_cast<const double2*>(sc + 8 * cb);
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-                const double t0 = sr[i] - c2.x, t1 = sr[i] - c2.y;
-                dist[i][cb][0] = fma(t0, t0, dist[i][cb][0]);
-                dist[i][cb][1] = fma(t1, t1, dist[i][cb][1]);
-            }
-        }
-    }
+    // the reference's shapes (d = 9: three steps; scalar models d = 2: one step) get the register-resident form
+    const int ks = cov_ksteps(d);
+#ifdef GGP_PHASES
+    unsigned long long tla__ = clock64();
+#endif
+    if (ks == 3) cov_dist<NU, 3>(dn, xr, SCB, sb, d, q, lane);
+    else if (ks == 1) cov_dist<NU, 1>(dn, xr, SCB, sb, d, q, lane);
+    else cov_dist<NU, 0>(dn, xr, SCB, sb, d, q, lane);
 #pragma unroll
     for (int i = 0; i < NU; ++i)
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
-            scr[(8 * i + 2 * cb) * 32 + lane] = -dist[i][cb][0];
-            scr[(8 * i + 2 * cb + 1) * 32 + lane] = -dist[i][cb][1];
+            scr[(8 * i + 2 * cb) * 32 + lane] = dn[i][cb][0];
+            scr[(8 * i + 2 * cb + 1) * 32 + lane] = dn[i][cb][1];
         }
-#pragma unroll 4
+#ifdef GGP_PHASES
+    if (dn[0][0][0] == 1.2345e300) tla__ = 0;
+#endif
+    LA_TICK(8);
+#pragma unroll 8
     for (int e = 0; e < 8 * NU; ++e) scr[e * 32 + lane] = exp_neg(scr[e * 32 + lane], etab);
+    LA_TICK(9);
 #pragma unroll
     for (int i = 0; i < NU; ++i)
 #pragma unroll
@@ -290,13 +397,29 @@ static __device__ __forceinline__ void pair_cov(double (&p)[2][4][2], const doub
         }
 }
 
-// scaled coordinates of the 32 columns of panel `row0` -> SC[k][32]; all threads, caller syncs
-static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SC, const double* __restrict__ X,
+// B fragments of the distance product for the 32 columns of panel `row0` -> SCB[s][cb][lane]; all threads, caller syncs
+static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SCB, const double* __restrict__ X,
                                                          const double* __restrict__ sb, int d, int m, int row0)
 {
-    for (int idx = threadIdx.x; idx < 32 * d; idx += blockDim.x) {
-        const int k = idx >> 5, c = idx & 31;
-        SC[idx] = (row0 + c < m) ? __ldg(X + (size_t)(row0 + c) * d + k) * sb[k] : 0.0;
+    const int n = sc_doubles(d);
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int s = idx >> 7, cb = (idx >> 5) & 3, ln = idx & 31;
+        const int k = 4 * s + (ln & 3), c = row0 + 8 * cb + (ln >> 2);
+        double v = 0.0;
+        if (c < m) {
+            const double* xc = X + (size_t)c * d;
+            if (k < d) v = 2.0 * (__ldg(xc + k) * sb[k]);
+            else if (k == d) v = -1.0;
+            else if (k == d + 1) {
+                double rr = 0.0;
+                for (int t = 0; t < d; ++t) {
+                    const double x = __ldg(xc + t) * sb[t];
+                    rr = fma(x, x, rr);
+                }
+                v = -rr;
+            }
+        }
+        SCB[idx] = v;
     }
 }
 
@@ -579,6 +702,354 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
     if (crank == 0 && tid == 0 && info) *info = 0;
     return sm.red[0];
 }
+
+// ---------------------------------------------------------------------------------------------
+// Look-ahead variant (one CTA per matrix).  The serial part of a panel -- the 32x32 diagonal-block
+// factorisation by one warp, its inverse and the w-block solve, ~30 k cycles during which the other warps
+// of the CTA used to wait -- is taken off the critical path: the diagonal block of panel j+1 is factored
+// while panel j is still being finished.  Stage jc (= j+1):
+//   warps 0,1: (a) "priority" pair: the rows of block jc in panel j (GEMM, covariance, TRSM, store), named
+//              barrier between the two warps; (b) look-ahead pair: block jc itself over k-blocks 0..j
+//              (GEMM, covariance) -> D; warp 0 factors it, then warp 0 solves the w block / stores the diagonal
+//              rows while warp 1 inverts the block (into D, copied to Minv at the next stage); (c) join the pool;
+//   warps 2,3: pool of the remaining 16-row pairs of panel j, handed out by a shared-memory counter.
+// Every matrix entry goes through the same arithmetic in the same order as in eval_block_loglik, so the
+// result is bit-identical to it (tests/test_gpu_core.py).  The pair body exists once (a small state machine
+// per warp) to keep the kernel's code size -- and instruction fetch -- where it was.
+// ---------------------------------------------------------------------------------------------
+struct LaSmem {
+    double* Minv;   // [32][MI_LD]  inverse of the diagonal block of the panel being finished (TRSM operand)
+    double* LT;     // [32][LT_LD]  LT[k][i] = L[i][k] of the block being factored
+    double* D;      // [32][D_LD]   P of the look-ahead block, then (after the factorisation) its inverse, D[i][k]
+    double* rdiag;  // [32]
+    double* uj;     // [2][32]      u blocks (by parity of the block index)
+    double* red;    // [8]
+    double* etab;   // [32]
+    double* wres;   // [Mp]
+    double* sb;     // [dpad]
+    double* SC;     // [2][sc_doubles(d)] B fragments of the distance product (by parity of the panel index)
+    double* scr;    // [NWARP][512] per-warp scratch of the covariance step
+    int* flag;      // [4]: 0 failure flag, 1 pool counter
+    int* soff;      // [Mp/8]
+    int scsz;
+};
+
+__host__ __device__ inline size_t la_smem_bytes(int Mp, int d) {
+    const int dpad = (d + 1) & ~1;
+    return (size_t)(32 * MI_LD + 32 * LT_LD + 32 * D_LD + 32 + 64 + 8 + 32 + Mp + dpad + 2 * sc_doubles(d) + NWARP * 512) * sizeof(double) +
+           16 + (size_t)(Mp / 8) * sizeof(int);
+}
+
+__device__ inline LaSmem carve_la_smem(unsigned char* base, int Mp, int d) {
+    LaSmem s;
+    const int dpad = (d + 1) & ~1;
+    double* p = reinterpret_cast<double*>(base);
+    s.Minv = p;     p += 32 * MI_LD;
+    s.LT = p;       p += 32 * LT_LD;
+    s.D = p;        p += 32 * D_LD;
+    s.rdiag = p;    p += 32;
+    s.uj = p;       p += 64;
+    s.red = p;      p += 8;
+    s.etab = p;     p += 32;
+    s.wres = p;     p += Mp;
+    s.sb = p;       p += dpad;
+    s.SC = p;       p += 2 * sc_doubles(d);
+    s.scr = p;      p += NWARP * 512;
+    s.flag = reinterpret_cast<int*>(p);
+    s.soff = s.flag + 4;
+    s.scsz = sc_doubles(d);
+    return s;
+}
+
+__device__ __forceinline__ void bar_pair01() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+// split producer / consumer forms for warps 0 and 1 (32 threads arrive, 32 wait)
+__device__ __forceinline__ void bar01_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar01_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, const double* __restrict__ X, int m, int Mp, int d,
+                                    const double* beta, double lamz, double diag_add,
+                                    const double* __restrict__ w, double* __restrict__ Lp,
+                                    double* __restrict__ u_out, int* info)
+{
+    static_assert(NWARP >= 2, "look-ahead variant needs at least two warps");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int nP = Mp >> 5;
+    const double inv_lamz = 1.0 / lamz;
+    const double diag = inv_lamz + diag_add;
+    double* __restrict__ D = sm.D;
+    double* __restrict__ LT = sm.LT;
+    double* __restrict__ wres = sm.wres;
+    double* __restrict__ scr = sm.scr + warp * 512;
+
+    __syncthreads();   // previous user of the shared buffers is done
+    if (tid < d) sm.sb[tid] = sqrt(beta[tid]);
+    for (int r = tid; r < Mp; r += NT) wres[r] = (r < m) ? w[r] : 0.0;
+    fill_exp_table(sm.etab);
+    fill_slab_offsets(sm.soff, Mp);
+    if (tid == 0) sm.flag[0] = 0;
+    double logdet = 0.0, quad = 0.0;    // partial sums, live in warp 0
+    __syncthreads();
+#ifdef GGP_PHASES
+    unsigned long long tla__ = clock64();
+#endif
+
+    for (int jc = 0; jc < nP; ++jc) {
+        const int j = jc - 1;                       // panel finished in this stage (none in stage 0)
+        if (j >= 0)                                 // inverse of block j, produced by the previous stage
+            for (int idx = tid; idx < 1024; idx += NT) sm.Minv[(idx >> 5) * MI_LD + (idx & 31)] = D[(idx >> 5) * D_LD + (idx & 31)];
+        fill_panel_coords(sm.SC + (jc & 1) * sm.scsz, X, sm.sb, d, m, jc << 5);
+        if (tid == 0) sm.flag[1] = 0;
+        LA_TICK(0);
+        __syncthreads();                                                         // (T)
+        LA_TICK(1);
+        const int nreg = (j >= 0) ? ((Mp - 32 * j) >> 3) - 8 : 0;               // pool units of panel j (multiple of 4)
+        int phase = (warp < 2) ? (j >= 0 ? 0 : 1) : 2;       // 0 priority pair, 1 look-ahead pair, 2 pool, 3 inverse (warp 1)
+        int pend = 0;        // warp 1: 1 = inverse of block jc still to do, 2 = do it after the pool pair in hand
+
+#pragma unroll 1
+        while (true) {
+            int cp = j, r0 = 0;
+            if (phase == 2) {
+                if (pend == 2) phase = 3;
+                else {
+                    int idx = 0;
+                    if (lane == 0) idx = atomicAdd(&sm.flag[1], 1);
+                    idx = __shfl_sync(0xffffffffu, idx, 0);
+                    if (2 * idx >= nreg) {
+                        if (pend == 0) break;
+                        phase = 3;
+                    } else {
+                        if (pend == 1) pend = 2;
+                        r0 = 32 * j + 64 + 16 * idx;
+                    }
+                }
+            } else {
+                cp = (phase == 0) ? j : jc;
+                r0 = 32 * jc + 16 * warp;
+            }
+            if (phase == 3) {
+                // warp 1 (after at most one pool pair, which overlaps warp 0's factorisation): inverse of block jc.
+                // Lane k solves Ljj y = e_k, rows in blocks of 8; result D[i][k] and the packed factor's inverse-block
+                // area (used by the prediction kernel)
+                LA_TICK(2);
+                bar01_wait(2);                                                   // (C) factor (LT, rdiag) or failure flag visible
+                LA_TICK(3);
+                if (sm.flag[0] == 0) {
+                    double* gm = Lp + minv_off(Mp) + 1024LL * jc;
+#pragma unroll 1
+                    for (int i0 = 0; i0 < 32; i0 += 8) {
+                        double y[8];
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) y[ii] = (i0 + ii == lane) ? 1.0 : 0.0;
+#pragma unroll 2
+                        for (int t = 0; t < i0; ++t) {
+                            const double yt = D[t * D_LD + lane];
+                            const double* lt = LT + t * LT_LD + i0;              // L[i0+ii][t]
+#pragma unroll
+                            for (int ii = 0; ii < 8; ii += 2) {
+                                const double2 l2 = *reinterpret_cast<const double2*>(lt + ii);
+                                y[ii] = fma(-l2.x, yt, y[ii]);
+                                y[ii + 1] = fma(-l2.y, yt, y[ii + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            y[ii] *= sm.rdiag[i0 + ii];
+#pragma unroll
+                            for (int i2 = ii + 1; i2 < 8; ++i2) y[i2] = fma(-LT[(i0 + ii) * LT_LD + i0 + i2], y[ii], y[i2]);
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            D[(i0 + ii) * D_LD + lane] = y[ii];
+                            gm[(i0 + ii) * 32 + lane] = y[ii];
+                        }
+                        __syncwarp();
+                    }
+                }
+                LA_TICK(4);
+                pend = 0;
+                phase = 2;
+                continue;
+            }
+            const int row0 = cp << 5;
+            const int rb[2] = {r0, r0 + 8};
+            double acc[2][4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
+            // ------------------------------------------------------------------ 1. DMMA update
+            LA_TICK(2);
+            if (cp > 0) panel_gemm<2>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, 0);
+#ifdef GGP_PHASES
+            if (acc[0][0][0] + acc[1][3][1] == 1.2345e300) tla__ = 0;
+#endif
+            LA_TICK(5);
+            // ------------------------------------------------------------------ 2. covariance, P = C - S (registers)
+            {
+                const int rr[2] = {rb[0] + g, rb[1] + g};
+                const bool ok[2] = {rr[0] < m, rr[1] < m};
+                pair_cov<2>(acc, X, rr, ok, sm.SC + (cp & 1) * sm.scsz, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane);
+            }
+#ifdef GGP_PHASES
+            if (acc[0][0][0] + acc[1][3][1] == 1.2345e300) tla__ = 0;
+#endif
+            LA_TICK(6);
+            if (phase == 1) {
+                // -------------------------------------------------------------- 3. diagonal block jc (look-ahead)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            D[(16 * warp + 8 * i + g) * D_LD + 8 * cb + 2 * q + e] = acc[i][cb][e];
+                if (warp == 1) {
+                    bar01_arrive(1);                                             // (B) this half of the block is in D
+                    pend = 1;                                                    // inverse after at most one pool pair
+                } else {
+                    LA_TICK(7);
+                    bar01_wait(1);                                               // (B) block complete in D
+                    LA_TICK(3);
+                    int failed;
+                    {
+                        // Cholesky of the 32x32 block, lane = row (same arithmetic as eval_block_loglik)
+                        double mypiv = 1.0;
+                        int bad = 0;
+#pragma unroll 1
+                        for (int k0 = 0; k0 < 32; k0 += 8) {
+                            double x[8];
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) x[kk] = D[lane * D_LD + k0 + kk];
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) {
+                                const int k = k0 + kk;
+                                if (lane == k) sm.red[2] = x[kk];
+                                __syncwarp();
+                                const double dk = sm.red[2];
+                                if (!(dk > 0.0) || !(dk < 1.0e300)) { if (!bad) bad = row0 + k + 1; }
+                                const double rk = rsqrt(dk);
+                                const double lik = (lane == k) ? dk * rk : x[kk] * rk;
+                                if (lane == k) mypiv = dk;
+                                x[kk] = lik;
+                                if (lane == 0) sm.rdiag[k] = rk;
+                                LT[k * LT_LD + lane] = (lane >= k) ? lik : 0.0;
+                                __syncwarp();
+#pragma unroll
+                                for (int k2 = kk + 1; k2 < 8; ++k2) x[k2] = fma(-lik, LT[k * LT_LD + k0 + k2], x[k2]);
+                            }
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) D[lane * D_LD + k0 + kk] = (lane >= k0 + kk) ? x[kk] : 0.0;
+#pragma unroll 2
+                            for (int c = k0 + 8; c < 32; ++c) {
+                                double a = D[lane * D_LD + c];
+#pragma unroll
+                                for (int kk = 0; kk < 8; ++kk) a = fma(-x[kk], LT[(k0 + kk) * LT_LD + c], a);
+                                D[lane * D_LD + c] = a;
+                            }
+                            __syncwarp();
+                            if (bad) break;
+                        }
+                        if (bad) { if (lane == 0) sm.flag[0] = bad; }
+                        else logdet += 0.5 * log(mypiv);
+
+                        failed = bad;
+                    }
+                    LA_TICK(10);
+                    bar01_arrive(2);                                             // (C) factor (LT, rdiag) or failure flag published
+                    if (!failed) {
+                    // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]  (L read from LT: D is being
+                    // overwritten with the inverse by warp 1)
+                    double b = wres[row0 + lane];
+                    double myu = 0.0;
+#pragma unroll 1
+                    for (int c = 0; c < 32; ++c) {
+                        const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
+                        if (lane == c) myu = uc;
+                        if (lane > c) b = fma(-LT[c * LT_LD + lane], uc, b);
+                    }
+                    sm.uj[(jc & 1) * 32 + lane] = myu;
+                    quad += myu * myu;
+                    if (u_out) u_out[row0 + lane] = myu;
+                    // diagonal rows of L (zeros above the diagonal) -> packed factor, panel jc
+                    double* __restrict__ Lpc = Lp + panel_off(jc, Mp);
+                    const int Rc = Mp - row0;
+#pragma unroll 1
+                    for (int ks = 0; ks < 4; ++ks) {
+                        double* dst = Lpc + (long long)ks * Rc * 8 + (long long)lane * 8;
+#pragma unroll
+                        for (int c = 0; c < 8; c += 2) {
+                            const int cc = 8 * ks + c;
+                            *reinterpret_cast<double2*>(dst + c) = make_double2(LT[cc * LT_LD + lane], LT[(cc + 1) * LT_LD + lane]);
+                        }
+                    }
+                    }
+                    LA_TICK(11);
+                }
+                phase = 2;
+            } else {
+                // -------------------------------------------------------------- 4. X = P Minv^T, store, update w (panel j)
+                double* __restrict__ Lpj = Lp + panel_off(j, Mp);
+                const int Rj = Mp - row0;
+                const double* __restrict__ ujj = sm.uj + (j & 1) * 32;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    double xt[4][2];
+                    unit_trsm(acc[i], xt, sm.Minv, g, q);
+                    const int r = rb[i] + g;
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        const double2 u2 = *reinterpret_cast<const double2*>(ujj + 8 * cb + 2 * q);
+                        s0 = fma(xt[cb][0], u2.x, s0);
+                        s1 = fma(xt[cb][1], u2.y, s1);
+                        *reinterpret_cast<double2*>(Lpj + (long long)cb * Rj * 8 + (long long)(r - row0) * 8 + 2 * q) =
+                            make_double2(xt[cb][0], xt[cb][1]);
+                    }
+                    double sdot = s0 + s1;
+                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+                    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+                    if (q == 0) wres[r] -= sdot;
+                }
+                LA_TICK(12);
+                if (phase == 0) {
+                    bar_pair01();                                                // (A) rows of block jc complete in panels 0..j
+                    phase = 1;
+                    LA_TICK(3);
+                }
+            }
+        }
+        LA_TICK(2);
+        __syncthreads();                                                         // (E)
+        LA_TICK(13);
+        if (sm.flag[0] != 0) {
+            if (tid == 0 && info) *info = sm.flag[0];
+            return -INFINITY;
+        }
+    }
+
+    if (warp == 0) {
+        double ld = warp_sum(logdet);
+        double qd = warp_sum(quad);
+        if (lane == 0) sm.red[0] = -ld - 0.5 * qd;
+    }
+    __syncthreads();
+    if (tid == 0 && info) *info = 0;
+    return sm.red[0];
+}
+
+// look-ahead variant on (default) / off: GGP_LOOKAHEAD=0 in the environment or ggp_set_lookahead(0) (tests, A/B runs)
+inline int& lookahead_flag()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GGP_LOOKAHEAD");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v;
+}
+inline bool use_lookahead() { return lookahead_flag() != 0; }
 
 // Cluster size for `ntasks` independent matrices: one CTA per matrix when the machine is already full, otherwise
 // the largest power of two that still fits all clusters in one wave of GGP_CTAS_PER_SM resident CTAs per SM: up to 8

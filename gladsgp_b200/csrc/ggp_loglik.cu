@@ -156,7 +156,7 @@ cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // (2) batched fused log-likelihood: one CTA per matrix.
 // ---------------------------------------------------------------------------------------------
-template <bool CL>
+template <bool CL, bool LA = false>
 __global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const double* __restrict__ W,
                       long long w_stride, const double* __restrict__ beta, const double* __restrict__ lamz,
@@ -164,11 +164,19 @@ loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const 
                       double* __restrict__ u_out, double* __restrict__ loglik, int* __restrict__ info)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
     const int b = CL ? blockIdx.x / cluster_nctarank() : blockIdx.x;
-    double ll = eval_block_loglik<CL>(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
-                                      W + (size_t)b * w_stride, Lws + (size_t)b * l_stride,
-                                      u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
+    double ll;
+    if constexpr (LA) {
+        LaSmem sm = carve_la_smem(smem_raw, Mp, d);
+        ll = eval_block_loglik_la(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
+                                  W + (size_t)b * w_stride, Lws + (size_t)b * l_stride,
+                                  u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
+    } else {
+        EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
+        ll = eval_block_loglik<CL>(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
+                                   W + (size_t)b * w_stride, Lws + (size_t)b * l_stride,
+                                   u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
+    }
     if (threadIdx.x == 0 && (!CL || cluster_ctarank() == 0)) loglik[b] = ll;
 }
 
@@ -246,6 +254,14 @@ int ggp_debug_phase_cycles(unsigned long long* out_host, int reset)
     if (reset) GGP_CUDA(cudaMemcpyToSymbol(ggp::g_phase, z, sizeof(z)));
     return GGP_OK;
 }
+int ggp_debug_phase2_cycles(unsigned long long* out_host, int reset)
+{
+    unsigned long long z[128] = {0};
+    GGP_CUDA(cudaDeviceSynchronize());
+    GGP_CUDA(cudaMemcpyFromSymbol(out_host, ggp::g_phase2, sizeof(z)));
+    if (reset) GGP_CUDA(cudaMemcpyToSymbol(ggp::g_phase2, z, sizeof(z)));
+    return GGP_OK;
+}
 #endif
 
 int ggp_debug_exp_neg_f64(const double* y, double* out, int n, void* stream)
@@ -257,6 +273,13 @@ int ggp_debug_exp_neg_f64(const double* y, double* out, int n, void* stream)
 }
 
 long long ggp_factor_doubles(int m) { return packed_doubles(round_up32(m)); }
+
+int ggp_set_lookahead(int on)
+{
+    const int old = lookahead_flag();
+    lookahead_flag() = on ? 1 : 0;
+    return old;
+}
 
 int ggp_padded_m(int m) { return round_up32(m); }
 
@@ -281,6 +304,16 @@ int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long 
         GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
         GGP_CUDA(launch_maybe_cluster(loglik_batched_kernel<true>, dim3(B * G), dim3(NT), smem, st, G, X, m, Mp, d, W, w_stride,
                                       beta, lamz, diag_add, factor_ws, ls, u_out, loglik_out, info_out));
+    } else if (use_lookahead()) {
+        const size_t sla = la_smem_bytes(Mp, d);
+        if (sla > 227 * 1024) {
+            set_error("ggp_loglik_batched_f64: m=%d d=%d needs %zu B of shared memory (> 227 KB)", m, d, sla);
+            return GGP_ERR_UNSUPPORTED;
+        }
+        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sla));
+        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(sla)));
+        loglik_batched_kernel<false, true><<<B, NT, sla, st>>>(X, m, Mp, d, W, w_stride, beta, lamz, diag_add, factor_ws, ls, u_out,
+                                                               loglik_out, info_out);
     } else {
         GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));

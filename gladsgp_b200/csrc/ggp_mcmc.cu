@@ -128,13 +128,27 @@ __device__ inline void gather_block_params(const ggp_mcmc_args& a, const double*
     diag_add = 1.0 / (chain_lamsim(a, c, j) * lamwos) + 1.0 / lamws;
 }
 
-template <bool CL>
+// one evaluation by the CTA (cluster): CL = cluster variant, LA = look-ahead variant (one CTA per matrix)
+template <bool CL, bool LA>
+static __device__ __forceinline__ double eval_dispatch(unsigned char* smem_raw, const double* __restrict__ X, int m, int Mp, int d,
+                                                       const double* beta, double lamz, double diag_add,
+                                                       const double* __restrict__ w, double* __restrict__ Lp)
+{
+    if constexpr (LA) {
+        LaSmem sm = carve_la_smem(smem_raw, Mp, d);
+        return eval_block_loglik_la(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr);
+    } else {
+        EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
+        return eval_block_loglik<CL>(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr);
+    }
+}
+
+template <bool CL, bool LA = false>
 __global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, int t)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Mp = round_up32(a.m);
-    EvalSmem sm = carve_eval_smem(smem_raw, Mp, a.d);
     __shared__ double beta_sm[64];
     const int j = CL ? blockIdx.x / cluster_nctarank() : blockIdx.x, c = blockIdx.y;
     const bool lead = (threadIdx.x == 0) && (!CL || cluster_ctarank() == 0);    // the one thread that owns the state
@@ -158,7 +172,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
         __syncthreads();
         gather_block_params(a, th, c, j, s, cand, beta_sm, lamz, diag_add);
         __syncthreads();
-        const double ll_new = eval_block_loglik<CL>(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, nullptr, nullptr);
+        const double ll_new = eval_dispatch<CL, LA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp);
         if (lead) {
             if (a.eval_count) atomicAdd(a.eval_count, 1ULL);
             const double ll_old = sig[j];
@@ -179,14 +193,13 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
 }
 
 // mode 0: sigwl <- per-PC terms of the current state.  mode 1: sigwl_cand <- terms under candidate lamWOs.
-template <bool CL>
+template <bool CL, bool LA = false>
 __global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
 eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride,
                 double* __restrict__ sig_cand, int mode)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Mp = round_up32(a.m);
-    EvalSmem sm = carve_eval_smem(smem_raw, Mp, a.d);
     __shared__ double beta_sm[64];
     const int j = CL ? blockIdx.x / cluster_nctarank() : blockIdx.x, c = blockIdx.y;
     const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
@@ -203,8 +216,7 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
     double lamz, diag_add;
     gather_block_params(a, th, c, j, site, cand, beta_sm, lamz, diag_add);
     __syncthreads();
-    const double ll = eval_block_loglik<CL>(sm, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, chain_w(a, c, j), Lp,
-                                            nullptr, nullptr);
+    const double ll = eval_dispatch<CL, LA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, chain_w(a, c, j), Lp);
     if (threadIdx.x == 0 && (!CL || cluster_ctarank() == 0)) {
         if (mode == 0) a.sigwl[(size_t)c * pu + j] = ll;
         else sig_cand[(size_t)c * pu + j] = ll;
@@ -301,13 +313,14 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         GGP_ARG(a.n_uniform >= 2 * P * a.n_steps, "uniform stream shorter than 2*P*n_steps");
     }
     const int Mp = round_up32(a.m);
-    const size_t smem = eval_smem_bytes(Mp, a.d);
+    int G = choose_cluster((long long)a.pu * a.n_chains, round_up32(a.m));
+    const bool la = (G == 1) && use_lookahead();
+    const size_t smem = la ? la_smem_bytes(Mp, a.d) : eval_smem_bytes(Mp, a.d);
     if (smem > 227 * 1024) {
         set_error("ggp_mcmc_run_f64: m=%d d=%d needs %zu B of shared memory (> 227 KB)", a.m, a.d, smem);
         return GGP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    int G = choose_cluster((long long)a.pu * a.n_chains, round_up32(a.m));
     const int cpct = eval_carveout_pct(smem);
     if (G > 1) {
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -316,6 +329,11 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
         G = checked_cluster(sweep_kernel<true>, G, smem);
         G = checked_cluster(eval_all_kernel<true>, G, smem);
+    } else if (la) {
+        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
     } else {
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
@@ -339,12 +357,14 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
 
     auto launch_eval_all = [&](int mode) -> cudaError_t {
         if (G > 1) return launch_maybe_cluster(eval_all_kernel<true>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode);
-        eval_all_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
+        if (la) eval_all_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
+        else eval_all_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
         return cudaSuccess;
     };
     auto launch_sweep = [&](int t) -> cudaError_t {
         if (G > 1) return launch_maybe_cluster(sweep_kernel<true>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, t);
-        sweep_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
+        if (la) sweep_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
+        else sweep_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
         return cudaSuccess;
     };
     if (a.init_sigwl) {

@@ -29,7 +29,7 @@ struct PredSmem {
 };
 
 __host__ __device__ inline size_t pred_smem_bytes(int d) {
-    return (size_t)(32 * MI_LD + 32 + 32 + 34 * ((d + 1) & ~1) + PNW * 512) * sizeof(double);
+    return (size_t)(32 * MI_LD + 32 + 32 + sc_doubles(d) + 2 * ((d + 1) & ~1) + PNW * 512) * sizeof(double);
 }
 
 // One CTA pushes blocks of PB test designs through the cached factor of block b.  Rows = designs: each
@@ -50,7 +50,7 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
         sm.Minv = p;  p += 32 * MI_LD;
         sm.uj = p;    p += 32;
         sm.etab = p;  p += 32;
-        sm.SC = p;    p += 32 * ((d + 1) & ~1);
+        sm.SC = p;    p += sc_doubles(d);
         sm.sb = p;    p += ((d + 1) & ~1);
         sm.scr = p;
     }

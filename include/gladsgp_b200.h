@@ -54,6 +54,9 @@ int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, co
 int ggp_debug_exp_neg_f64(const double* y, double* out, int n, void* stream);
 long long ggp_factor_doubles(int m);
 int ggp_padded_m(int m);
+/* one-CTA-per-matrix evaluations use the look-ahead schedule (default 1; GGP_LOOKAHEAD=0 in the environment turns it
+ * off): both schedules and the cluster variant give bit-identical results.  Returns the previous setting. */
+int ggp_set_lookahead(int on);
 int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long long w_stride,
                            const double* beta, const double* lamz, const double* diag_add, int B,
                            double* factor_ws, double* u_out, double* loglik_out, int* info_out, void* stream);

@@ -192,3 +192,38 @@ def test_cluster_and_single_cta_variants_agree_bitwise(cuda, monkeypatch):
     monkeypatch.setenv('GGP_CLUSTER', '8')
     bad = ops.loglik_batched(num.zt, W, np.full((2, num.d), 1e-6), np.ones(2), np.full(2, -0.999999))
     assert np.all(bad['loglik'].cpu().numpy() == -np.inf) and np.all(bad['info'].cpu().numpy() > 0)
+
+
+@pytest.mark.parametrize('m,q,pu', [(32, 2, 1), (100, 8, 3), (257, 4, 2), (512, 8, 2)])
+def test_lookahead_and_plain_schedules_agree_bitwise(cuda, monkeypatch, m, q, pu):
+    """The look-ahead schedule (diagonal block of panel j+1 factored while panel j is finished; dynamic pool of pairs)
+    reorders work, not arithmetic: factor, u and log-likelihood equal the plain schedule and the cluster variant bit for bit."""
+    from gladsgp_b200 import ops, _lib
+    h = _lib.load()
+    pr = make_problem(m=m, q=q, pu=pu)
+    num = pr['num']
+    beta, lamz, lamws, lamwos = random_hypers(num, pu, seed=11)
+    dadd = 1.0 / (num.LamSim * lamwos) + 1.0 / lamws
+    W = num.w.T.copy()
+    res = {}
+    old = h.ggp_set_lookahead(1)
+    try:
+        for key, g, la in (('la', '1', 1), ('plain', '1', 0), ('cluster', '4', 0)):
+            monkeypatch.setenv('GGP_CLUSTER', g)
+            h.ggp_set_lookahead(la)
+            out = ops.loglik_batched(num.zt, W, beta, lamz, dadd, want_factor=True, want_u=True)
+            res[key] = (out['loglik'].cpu().numpy(), ops.factor_unpack(out['factor'], m).cpu().numpy(), out['u'].cpu().numpy())
+        for key in ('plain', 'cluster'):
+            for a, b in zip(res['la'], res[key]):
+                assert np.array_equal(a, b), key
+        # not positive definite: same failing pivot reported
+        monkeypatch.setenv('GGP_CLUSTER', '1')
+        infos = []
+        for la in (1, 0):
+            h.ggp_set_lookahead(la)
+            bad = ops.loglik_batched(num.zt, W, np.full((pu, num.d), 1e-6), np.ones(pu), np.full(pu, -0.999999))
+            assert np.all(bad['loglik'].cpu().numpy() == -np.inf)
+            infos.append(bad['info'].cpu().numpy())
+        assert np.array_equal(infos[0], infos[1]) and np.all(infos[0] > 0)
+    finally:
+        h.ggp_set_lookahead(old)

@@ -4,7 +4,7 @@ import ctypes as C, os, subprocess, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-so = os.path.join(ROOT, 'gpurun_out', 'libggp_phases.so')
+so = os.path.join(ROOT, 'build_var', 'libggp_phases.so')
 if not os.path.exists(so):
     raise SystemExit('build first: nvcc -DGGP_PHASES ... (see tools/build_phases.sh)')
 from gladsgp_b200 import _lib
