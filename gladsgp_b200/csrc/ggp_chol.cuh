@@ -165,13 +165,12 @@ __device__ inline void fill_slab_offsets(int* soff, int Mp)
 #ifndef GGP_RB
 #define GGP_RB 2          // same for the B fragments
 #endif
-template <int NU>
+template <int NU, int RA = GGP_RA, int RB = GGP_RB>
 static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const double* __restrict__ Ap,
                                                   const double* __restrict__ Lb, const int* __restrict__ soff, int j,
                                                   int row0, const int (&rb)[2], int g, int q, int a_ld)
 {
     constexpr int PD = 2;                    // prefetch distance in k-blocks (4 sub-slabs each)
-    constexpr int RA = GGP_RA, RB = GGP_RB;
     static_assert(4 % RA == 0 && 4 % RB == 0, "ring depths must divide the 4 sub-slabs of a k-block");
     const int lane = 4 * g + q;
     const int nsub = 4 * j;
@@ -361,14 +360,18 @@ static __device__ __forceinline__ void pair_cov(double (&p)[2][4][2], const doub
         for (int cb = 0; cb < 4; ++cb) { dn[i][cb][0] = 0.0; dn[i][cb][1] = 0.0; }
         xr[i] = Xr + (size_t)((i < NU && row_ok[i]) ? r[i] : 0) * d;
     }
-    // the reference's shapes (d = 9: three steps; scalar models d = 2: one step) get the register-resident form
     const int ks = cov_ksteps(d);
 #ifdef GGP_PHASES
     unsigned long long tla__ = clock64();
 #endif
-    if (ks == 3) cov_dist<NU, 3>(dn, xr, SCB, sb, d, q, lane);
-    else if (ks == 1) cov_dist<NU, 1>(dn, xr, SCB, sb, d, q, lane);
-    else cov_dist<NU, 0>(dn, xr, SCB, sb, d, q, lane);
+    switch (ks) {       // d <= 18 (every configuration of the reference: d = 2 -> 1 step, 9 -> 3, 17 -> 5): register-resident form
+        case 1: cov_dist<NU, 1>(dn, xr, SCB, sb, d, q, lane); break;
+        case 2: cov_dist<NU, 2>(dn, xr, SCB, sb, d, q, lane); break;
+        case 3: cov_dist<NU, 3>(dn, xr, SCB, sb, d, q, lane); break;
+        case 4: cov_dist<NU, 4>(dn, xr, SCB, sb, d, q, lane); break;
+        case 5: cov_dist<NU, 5>(dn, xr, SCB, sb, d, q, lane); break;
+        default: cov_dist<NU, 0>(dn, xr, SCB, sb, d, q, lane); break;
+    }
 #pragma unroll
     for (int i = 0; i < NU; ++i)
 #pragma unroll
@@ -397,7 +400,9 @@ static __device__ __forceinline__ void pair_cov(double (&p)[2][4][2], const doub
         }
 }
 
-// B fragments of the distance product for the 32 columns of panel `row0` -> SCB[s][cb][lane]; all threads, caller syncs
+// B fragments of the distance product for the 32 columns of panel `row0` -> SCB[s][cb][lane]; all threads of the CTA
+// (contains a __syncthreads: the column norms are summed from the scaled coordinates already in shared memory, not
+// from d dependent global loads); caller syncs afterwards
 static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SCB, const double* __restrict__ X,
                                                          const double* __restrict__ sb, int d, int m, int row0)
 {
@@ -407,19 +412,23 @@ static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SC
         const int k = 4 * s + (ln & 3), c = row0 + 8 * cb + (ln >> 2);
         double v = 0.0;
         if (c < m) {
-            const double* xc = X + (size_t)c * d;
-            if (k < d) v = 2.0 * (__ldg(xc + k) * sb[k]);
+            if (k < d) v = 2.0 * (__ldg(X + (size_t)c * d + k) * sb[k]);
             else if (k == d) v = -1.0;
-            else if (k == d + 1) {
-                double rr = 0.0;
-                for (int t = 0; t < d; ++t) {
-                    const double x = __ldg(xc + t) * sb[t];
-                    rr = fma(x, x, rr);
-                }
-                v = -rr;
-            }
         }
         SCB[idx] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int cc = threadIdx.x;                          // column of the panel: cb = cc / 8, g = cc % 8
+        if (row0 + cc < m) {
+            double rr = 0.0;
+            for (int t = 0; t < d; ++t) {
+                const double x = 0.5 * SCB[(t >> 2) * 128 + (cc >> 3) * 32 + (cc & 7) * 4 + (t & 3)];
+                rr = fma(x, x, rr);
+            }
+            const int k = d + 1;
+            SCB[(k >> 2) * 128 + (cc >> 3) * 32 + (cc & 7) * 4 + (k & 3)] = -rr;
+        }
     }
 }
 
@@ -431,7 +440,9 @@ static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SC
 // 8-row units are dealt round-robin to the G*NWARP warps, CTA 0 owns the diagonal block and publishes Minv / u
 // through global memory, panels are separated by cluster barriers (release/acquire), the running forward solve
 // of w lives in global memory.  Only CTA 0 returns the value.
-template <bool CL = false>
+// RA: register ring depth of the A fragments in the pair GEMM (cluster kernels, 168 registers per thread: 4 for matrices up
+// to 1024 rows -- single-chain cfg3 +5 % -- and 2 above, where the deeper ring measured 10 % slower)
+template <bool CL = false, int RA = GGP_RA>
 static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, const double* __restrict__ X, int m, int Mp, int d,
                                     const double* beta, double lamz, double diag_add,
                                     const double* __restrict__ w, double* __restrict__ Lp,
@@ -496,7 +507,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
             // ------------------------------------------------------------------ 1. DMMA update
             GGP_TICKW(2, 23, acc[0][0][0]);
             if (j > 0) {
-                if (nu == 2) panel_gemm<2>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
+                if (nu == 2) panel_gemm<2, RA>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
                 else if (nu == 1) panel_gemm<1>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
             }
             GGP_TICKW(2, 20, acc[0][0][0] + acc[1][3][1] + acc[0][3][1] + acc[1][0][0]);
@@ -1052,7 +1063,7 @@ inline int& lookahead_flag()
 inline bool use_lookahead() { return lookahead_flag() != 0; }
 
 // Cluster size for `ntasks` independent matrices: one CTA per matrix when the machine is already full, otherwise
-// the largest power of two that still fits all clusters in one wave of GGP_CTAS_PER_SM resident CTAs per SM: up to 8
+// the largest power of two that still fits all clusters in one wave of GGP_CL_CTAS_PER_SM resident CTAs per SM: up to 8
 // (the portable cluster limit), 16 for matrices of 1024 rows and more (cfg 5: one chain of 20 PCs at m = 4096 runs
 // 0.80 -> 0.55 s per step).  GGP_CLUSTER=<n> overrides (developer experiments).
 inline int choose_cluster(long long ntasks, int Mp)
@@ -1064,7 +1075,7 @@ inline int choose_cluster(long long ntasks, int Mp)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long slots = (long long)sms * GGP_CTAS_PER_SM;
+    const long long slots = (long long)sms * GGP_CL_CTAS_PER_SM;      // resident CTAs of the cluster kernels
     const int gmax = (Mp >= 1024) ? 16 : 8;
     int g = 1;
     while (g < gmax && ntasks * (g * 2) <= slots) g *= 2;

@@ -156,8 +156,8 @@ cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // (2) batched fused log-likelihood: one CTA per matrix.
 // ---------------------------------------------------------------------------------------------
-template <bool CL, bool LA = false>
-__global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
+template <bool CL, bool LA = false, int RA = GGP_RA>
+__global__ void __launch_bounds__(NT, CL ? GGP_CL_CTAS_PER_SM : GGP_CTAS_PER_SM)
 loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const double* __restrict__ W,
                       long long w_stride, const double* __restrict__ beta, const double* __restrict__ lamz,
                       const double* __restrict__ diag_add, double* __restrict__ Lws, long long l_stride,
@@ -173,7 +173,7 @@ loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const 
                                   u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
     } else {
         EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
-        ll = eval_block_loglik<CL>(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
+        ll = eval_block_loglik<CL, RA>(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
                                    W + (size_t)b * w_stride, Lws + (size_t)b * l_stride,
                                    u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
     }
@@ -299,11 +299,16 @@ int ggp_loglik_batched_f64(const double* X, int m, int d, const double* W, long 
     int G = choose_cluster(B, round_up32(m));
     const long long ls = packed_doubles(Mp);
     if (G > 1) {
-        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        G = checked_cluster(loglik_batched_kernel<true>, G, smem);
-        GGP_CUDA(cudaFuncSetAttribute(loglik_batched_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
-        GGP_CUDA(launch_maybe_cluster(loglik_batched_kernel<true>, dim3(B * G), dim3(NT), smem, st, G, X, m, Mp, d, W, w_stride,
-                                      beta, lamz, diag_add, factor_ws, ls, u_out, loglik_out, info_out));
+        auto run = [&](auto kern) -> int {
+            GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int Gc = checked_cluster(kern, G, smem);
+            GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
+            GGP_CUDA(launch_maybe_cluster(kern, dim3(B * Gc), dim3(NT), smem, st, Gc, X, m, Mp, d, W, w_stride,
+                                          beta, lamz, diag_add, factor_ws, ls, u_out, loglik_out, info_out));
+            return GGP_OK;
+        };
+        const int rc = (Mp <= 1024) ? run(loglik_batched_kernel<true, false, 4>) : run(loglik_batched_kernel<true, false, 2>);
+        if (rc != GGP_OK) return rc;
     } else if (use_lookahead()) {
         const size_t sla = la_smem_bytes(Mp, d);
         if (sla > 227 * 1024) {

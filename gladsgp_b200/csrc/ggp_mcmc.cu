@@ -129,7 +129,7 @@ __device__ inline void gather_block_params(const ggp_mcmc_args& a, const double*
 }
 
 // one evaluation by the CTA (cluster): CL = cluster variant, LA = look-ahead variant (one CTA per matrix)
-template <bool CL, bool LA>
+template <bool CL, bool LA, int RA>
 static __device__ __forceinline__ double eval_dispatch(unsigned char* smem_raw, const double* __restrict__ X, int m, int Mp, int d,
                                                        const double* beta, double lamz, double diag_add,
                                                        const double* __restrict__ w, double* __restrict__ Lp)
@@ -139,12 +139,12 @@ static __device__ __forceinline__ double eval_dispatch(unsigned char* smem_raw, 
         return eval_block_loglik_la(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr);
     } else {
         EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
-        return eval_block_loglik<CL>(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr);
+        return eval_block_loglik<CL, RA>(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr);
     }
 }
 
-template <bool CL, bool LA = false>
-__global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
+template <bool CL, bool LA = false, int RA = GGP_RA>
+__global__ void __launch_bounds__(NT, CL ? GGP_CL_CTAS_PER_SM : GGP_CTAS_PER_SM)
 sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, int t)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -172,7 +172,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
         __syncthreads();
         gather_block_params(a, th, c, j, s, cand, beta_sm, lamz, diag_add);
         __syncthreads();
-        const double ll_new = eval_dispatch<CL, LA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp);
+        const double ll_new = eval_dispatch<CL, LA, RA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp);
         if (lead) {
             if (a.eval_count) atomicAdd(a.eval_count, 1ULL);
             const double ll_old = sig[j];
@@ -193,8 +193,8 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
 }
 
 // mode 0: sigwl <- per-PC terms of the current state.  mode 1: sigwl_cand <- terms under candidate lamWOs.
-template <bool CL, bool LA = false>
-__global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
+template <bool CL, bool LA = false, int RA = GGP_RA>
+__global__ void __launch_bounds__(NT, CL ? GGP_CL_CTAS_PER_SM : GGP_CTAS_PER_SM)
 eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride,
                 double* __restrict__ sig_cand, int mode)
 {
@@ -216,7 +216,7 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
     double lamz, diag_add;
     gather_block_params(a, th, c, j, site, cand, beta_sm, lamz, diag_add);
     __syncthreads();
-    const double ll = eval_dispatch<CL, LA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, chain_w(a, c, j), Lp);
+    const double ll = eval_dispatch<CL, LA, RA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, chain_w(a, c, j), Lp);
     if (threadIdx.x == 0 && (!CL || cluster_ctarank() == 0)) {
         if (mode == 0) a.sigwl[(size_t)c * pu + j] = ll;
         else sig_cand[(size_t)c * pu + j] = ll;
@@ -322,13 +322,20 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int cpct = eval_carveout_pct(smem);
+    const bool deep = Mp <= 1024;          // cluster kernels: A-fragment ring depth 4 (see eval_block_loglik)
     if (G > 1) {
-        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
-        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
-        G = checked_cluster(sweep_kernel<true>, G, smem);
-        G = checked_cluster(eval_all_kernel<true>, G, smem);
+        auto prep = [&](auto sweep, auto evall) -> int {
+            GGP_CUDA(cudaFuncSetAttribute(sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GGP_CUDA(cudaFuncSetAttribute(sweep, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+            GGP_CUDA(cudaFuncSetAttribute(evall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GGP_CUDA(cudaFuncSetAttribute(evall, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+            G = checked_cluster(sweep, G, smem);
+            G = checked_cluster(evall, G, smem);
+            return GGP_OK;
+        };
+        const int rc = deep ? prep(sweep_kernel<true, false, 4>, eval_all_kernel<true, false, 4>)
+                            : prep(sweep_kernel<true, false, 2>, eval_all_kernel<true, false, 2>);
+        if (rc != GGP_OK) return rc;
     } else if (la) {
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
@@ -356,13 +363,15 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     const int cb = (a.n_chains + 31) / 32;
 
     auto launch_eval_all = [&](int mode) -> cudaError_t {
-        if (G > 1) return launch_maybe_cluster(eval_all_kernel<true>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode);
+        if (G > 1) return deep ? launch_maybe_cluster(eval_all_kernel<true, false, 4>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode)
+                               : launch_maybe_cluster(eval_all_kernel<true, false, 2>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode);
         if (la) eval_all_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
         else eval_all_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
         return cudaSuccess;
     };
     auto launch_sweep = [&](int t) -> cudaError_t {
-        if (G > 1) return launch_maybe_cluster(sweep_kernel<true>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, t);
+        if (G > 1) return deep ? launch_maybe_cluster(sweep_kernel<true, false, 4>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, t)
+                               : launch_maybe_cluster(sweep_kernel<true, false, 2>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, t);
         if (la) sweep_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
         else sweep_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
         return cudaSuccess;
