@@ -425,3 +425,30 @@ def rsvd_xty_tc(X, Y):
     Bt = torch.empty((r, n), dtype=torch.float32, device='cuda')
     check(lib.ggp_rsvd_xty_tc_f32(ptr(X), m, n, ptr(Y.contiguous()), r, ptr(Bt), stream_ptr()), 'ggp_rsvd_xty_tc_f32')
     return Bt
+
+
+def sobol_upload(f_A, f_B, f_AB):
+    """Function values of the Saltelli scheme -> device (f_A, f_B (N,p); f_AB (n_dim,N,p)), float64."""
+    torch = _lib.require_cuda()
+    return tuple(torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), device='cuda') for a in (f_A, f_B, f_AB))
+
+
+def sobol_stats(dev, N, p, n_dim, idx=None, clamp=True):
+    """First-order / total Saltelli statistics of R index sets (src/utils.py:97-118): two (R,p,n_dim) host arrays.
+    idx (R,n) integers in [0,N) or None (one set: the full sample)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    fA, fB, fAB = dev
+    if idx is None:
+        R, n, it = 1, N, None
+    else:
+        idx = np.asarray(idx)
+        if idx.ndim != 2 or idx.size == 0 or idx.min() < 0 or idx.max() >= N:
+            raise ValueError('idx must be a non-empty (R, n) array of indices in [0, N)')
+        R, n = idx.shape
+        it = torch.as_tensor(np.ascontiguousarray(idx.astype(np.int32)), device='cuda')
+    first = torch.empty((R, p, n_dim), dtype=torch.float64, device='cuda')
+    total = torch.empty((R, p, n_dim), dtype=torch.float64, device='cuda')
+    check(lib.ggp_sobol_stats_f64(ptr(fA), ptr(fB), ptr(fAB), N, p, n_dim, ptr(it), n, n, R, 1 if clamp else 0,
+                                  ptr(first), ptr(total), stream_ptr()), 'ggp_sobol_stats_f64')
+    return first.cpu().numpy(), total.cpu().numpy()

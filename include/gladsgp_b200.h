@@ -160,6 +160,17 @@ int ggp_reconstruct_stats_f32(const float* w, const float* K, const float* sd, i
                               int mean_len, const float* noise, int nsamp, int npred, int pu, long long n_y, double q,
                               float* ymean_out, float* ylo_out, float* yhi_out, void* stream);
 
+/* ---- Sobol' / Saltelli sensitivity statistics --------------------------------
+ * src/utils.py:80-92 (point estimates), :97-118 and :213-243 (the statistics scipy.stats.bootstrap evaluates 9999 times and
+ * the BCa jackknife N times; callers sensitivity_indices.py:96,214).  For each of R index sets ids (n entries of 0..N-1;
+ * idx null = the identity set 0..n-1):
+ *   var = population variance of [f_A[ids], f_B[ids]] per output;  V = mean(f_A (f_AB - f_B));  E = mean((f_B - f_AB)^2)/2
+ *   first[r][out][i] = V/var,  total[r][out][i] = E/var   (V, E clamped at 0 iff clamp, as in the reference's bootstrap statistics)
+ * fA, fB [N][p]; fAB [n_dim][N][p]; idx [R][idx_stride] int32; outputs [R][p][n_dim]. */
+int ggp_sobol_stats_f64(const double* fA, const double* fB, const double* fAB, int N, int p, int n_dim,
+                        const int* idx, long long idx_stride, int n, int R, int clamp,
+                        double* first_out, double* total_out, void* stream);
+
 /* ---- (4) randomized SVD passes -----------------------------------------------------------------
  * src/svd.py:52  Y = X @ omega           -> ggp_rsvd_sketch_f32 (OmegaT = omega^T, [r][n])
  * src/svd.py:56  Y = X @ X.T @ Y         -> ggp_rsvd_xty_f32 then ggp_rsvd_sketch_f32 (X (X^T Y))
