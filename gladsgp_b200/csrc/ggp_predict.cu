@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(256)
 reconstruct_stats_kernel(const float* __restrict__ w, const float* __restrict__ K, const float* __restrict__ sd,
                          int sd_len, const float* __restrict__ mu, int mu_len, const float* __restrict__ noise,
                          int nsamp, int npred, int pu, long long n_y, int i0, float frac,
-                         float* __restrict__ ymean, float* __restrict__ ylo, float* __restrict__ yhi)
+                         float* __restrict__ ymean, float* __restrict__ ylo, float* __restrict__ yhi,
+                         const float* __restrict__ ytest, float mape_floor, double* __restrict__ err_part)
 {
     extern __shared__ __align__(16) float ws[];          // [nsamp][PUMAX] then noise [nsamp]
     float* ns = ws + (size_t)nsamp * PUMAX;
@@ -314,6 +315,8 @@ reconstruct_stats_kernel(const float* __restrict__ w, const float* __restrict__ 
         }
     }
     const float inv_n = 1.f / (float)nsamp;
+    // error statistics against the test field (assess_all_models.py:523-538), accumulated in FP64 per thread
+    double e_sq = 0.0, e_ape = 0.0, e_cnt = 0.0, e_cov = 0.0, e_lo = 0.0, e_hi = 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         if (col[c] < n_y) {
@@ -322,26 +325,68 @@ reconstruct_stats_kernel(const float* __restrict__ w, const float* __restrict__ 
             for (int k = 0; k < KQ - 1; ++k)
                 if (k == i0) { a = lo[c][k]; b = lo[c][k + 1]; ha = hi[c][k + 1]; hb = hi[c][k]; }
             const size_t o = (size_t)t * n_y + col[c];
-            __stcs(ymean + o, sum[c] * inv_n);
-            __stcs(ylo + o, a + (b - a) * frac);
-            __stcs(yhi + o, ha + (hb - ha) * (1.f - frac));
+            const float vm = sum[c] * inv_n, vl = a + (b - a) * frac, vh = ha + (hb - ha) * (1.f - frac);
+            if (ymean) {
+                __stcs(ymean + o, vm);
+                __stcs(ylo + o, vl);
+                __stcs(yhi + o, vh);
+            }
+            if (ytest) {
+                const float yt = __ldcs(ytest + o);
+                const float res = vm - yt;
+                e_sq += (double)(res * res);
+                if (!(yt < mape_floor)) { e_ape += (double)fabsf(res / yt); e_cnt += 1.0; }
+                if (yt >= vl && yt <= vh) e_cov += 1.0;
+                e_lo += (double)vl;
+                e_hi += (double)vh;
+            }
         }
     }
+    if (ytest) {
+        // fixed-order block reduction -> one partial row per CTA (summed in order by errstats_reduce_kernel)
+        __shared__ double red[8][6];
+        double v[6] = {e_sq, e_ape, e_cnt, e_cov, e_lo, e_hi};
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((tid & 31) == 0)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) red[tid >> 5][k] = v[k];
+        __syncthreads();
+        if (tid < 6) {
+            double sacc = 0.0;
+            for (int wv = 0; wv < 8; ++wv) sacc += red[wv][tid];
+            err_part[((size_t)t * gridDim.x + blockIdx.x) * 6 + tid] = sacc;
+        }
+    }
+}
+
+// err[t][k] = sum over the column tiles of err_part[t][tile][k], in tile order
+__global__ void errstats_reduce_kernel(const double* __restrict__ part, int ntile, int npred, double* __restrict__ err)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npred * 6) return;
+    const int t = idx / 6, k = idx - 6 * t;
+    double sacc = 0.0;
+    for (int b = 0; b < ntile; ++b) sacc += part[((size_t)t * ntile + b) * 6 + k];
+    err[idx] = sacc;
 }
 
 template <int PUMAX>
 static int launch_stats(const float* w, const float* K, const float* sd, int sd_len, const float* mean, int mean_len,
                         const float* noise, int nsamp, int npred, int pu, long long n_y, int i0, float frac,
-                        float* ymean, float* ylo, float* yhi, cudaStream_t st)
+                        float* ymean, float* ylo, float* yhi, cudaStream_t st,
+                        const float* ytest = nullptr, float mape_floor = 0.f, double* err_part = nullptr)
 {
     const dim3 grid((unsigned)((n_y + RC_COLS - 1) / RC_COLS), (unsigned)npred);
     const size_t smem = ((size_t)nsamp * PUMAX + nsamp) * sizeof(float);
     if (i0 + 2 <= 4)
         reconstruct_stats_kernel<PUMAX, 4><<<grid, 256, smem, st>>>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu,
-                                                                   n_y, i0, frac, ymean, ylo, yhi);
+                                                                   n_y, i0, frac, ymean, ylo, yhi, ytest, mape_floor, err_part);
     else
         reconstruct_stats_kernel<PUMAX, 8><<<grid, 256, smem, st>>>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu,
-                                                                   n_y, i0, frac, ymean, ylo, yhi);
+                                                                   n_y, i0, frac, ymean, ylo, yhi, ytest, mape_floor, err_part);
     return 0;
 }
 
@@ -467,6 +512,48 @@ int ggp_reconstruct_stats_f32(const float* w, const float* K, const float* sd, i
     else if (pu <= 8) launch_stats<8>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st);
     else if (pu <= 12) launch_stats<12>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st);
     else launch_stats<16>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st);
+    GGP_CUDA(cudaGetLastError());
+    return GGP_OK;
+}
+
+long long ggp_errstats_workspace_bytes(int npred, long long n_y)
+{
+    if (npred <= 0 || n_y <= 0) return -1;
+    return (long long)npred * ((n_y + RC_COLS - 1) / RC_COLS) * 6 * (long long)sizeof(double);
+}
+
+int ggp_reconstruct_errstats_f32(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
+                                 int mean_len, const float* noise, int nsamp, int npred, int pu, long long n_y, double q,
+                                 const float* y_test, float mape_floor, float* ymean_out, float* ylo_out, float* yhi_out,
+                                 double* err_out, void* workspace, long long workspace_bytes, void* stream)
+{
+    GGP_ARG(w && K && sd && mean && y_test && err_out && workspace, "null pointer");
+    GGP_ARG((ymean_out && ylo_out && yhi_out) || (!ymean_out && !ylo_out && !yhi_out), "field outputs: all three or none");
+    GGP_ARG(nsamp > 1 && npred > 0 && pu > 0 && n_y > 0, "nsamp, npred, pu, n_y must be positive");
+    GGP_ARG((sd_len == 1 || sd_len == n_y) && (mean_len == 1 || mean_len == n_y), "sd/mean length must be 1 or n_y");
+    GGP_ARG(q > 0.0 && q < 0.5, "q must be in (0, 0.5)");
+    GGP_ARG(npred <= 65535, "npred must be <= 65535 per call");
+    const double pos = q * (nsamp - 1);
+    const int i0 = (int)floor(pos);
+    const float frac = (float)(pos - i0);
+    if (pu > 16 || i0 + 2 > 8 || i0 + 2 > nsamp || (size_t)nsamp * 17 * sizeof(float) > 200 * 1024) {
+        set_error("ggp_reconstruct_errstats_f32: unsupported (pu=%d > 16 or quantile needs %d > 8 order statistics)", pu, i0 + 2);
+        return GGP_ERR_UNSUPPORTED;
+    }
+    const long long need = ggp_errstats_workspace_bytes(npred, n_y);
+    if (workspace_bytes < need) {
+        set_error("ggp_reconstruct_errstats_f32: workspace too small (%lld < %lld)", workspace_bytes, need);
+        return GGP_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* part = reinterpret_cast<double*>(workspace);
+    if (pu <= 4) launch_stats<4>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st, y_test, mape_floor, part);
+    else if (pu <= 8) launch_stats<8>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st, y_test, mape_floor, part);
+    else if (pu <= 12) launch_stats<12>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st, y_test, mape_floor, part);
+    else launch_stats<16>(w, K, sd, sd_len, mean, mean_len, noise, nsamp, npred, pu, n_y, i0, frac, ymean_out, ylo_out, yhi_out, st, y_test, mape_floor, part);
+    GGP_CUDA(cudaGetLastError());
+    const int ntile = (int)((n_y + RC_COLS - 1) / RC_COLS);
+    errstats_reduce_kernel<<<(npred * 6 + 127) / 128, 128, 0, st>>>(part, ntile, npred, err_out);
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }

@@ -452,3 +452,31 @@ def sobol_stats(dev, N, p, n_dim, idx=None, clamp=True):
     check(lib.ggp_sobol_stats_f64(ptr(fA), ptr(fB), ptr(fAB), N, p, n_dim, ptr(it), n, n, R, 1 if clamp else 0,
                                   ptr(first), ptr(total), stream_ptr()), 'ggp_sobol_stats_f64')
     return first.cpu().numpy(), total.cpu().numpy()
+
+
+def reconstruct_errstats(w, K, sd, mean, y_test, mape_floor, q=0.025, noise=None, want_fields=False):
+    """reconstruct_stats with the test-error sums of assess_all_models.py:523-538 fused in.
+    y_test (npred, n_y) f32 (device tensor or array).  Returns (err (npred, 6) float64 host array, fields or None):
+    err columns = sum resid^2, sum |resid / y_test| over y_test >= mape_floor, count of those, covered count, sum lq, sum uq."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = 'cuda'
+
+    def f32(t):
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.ascontiguousarray(np.asarray(t, dtype=np.float32)))
+        return t.to(device=dev, dtype=torch.float32).contiguous()
+    w = f32(w); K = f32(K); sd = f32(sd).reshape(-1); mean = f32(mean).reshape(-1)
+    nsamp, npred, pu = w.shape
+    n_y = K.shape[1]
+    yt = f32(y_test).reshape(npred, n_y)
+    nz = None if noise is None else f32(noise).reshape(nsamp, npred)
+    outs = [torch.empty((npred, n_y), dtype=torch.float32, device=dev) for _ in range(3)] if want_fields else [None] * 3
+    need = lib.ggp_errstats_workspace_bytes(npred, n_y)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    err = torch.empty((npred, 6), dtype=torch.float64, device=dev)
+    check(lib.ggp_reconstruct_errstats_f32(ptr(w), ptr(K), ptr(sd), sd.numel(), ptr(mean), mean.numel(), ptr(nz), nsamp,
+                                           npred, pu, n_y, float(q), ptr(yt), float(mape_floor), ptr(outs[0]), ptr(outs[1]),
+                                           ptr(outs[2]), ptr(err), ptr(ws), need, stream_ptr()),
+          'ggp_reconstruct_errstats_f32')
+    return err.cpu().numpy(), (tuple(outs) if want_fields else None)

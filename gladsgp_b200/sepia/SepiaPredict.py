@@ -187,6 +187,38 @@ class SepiaEmulatorPrediction(SepiaPrediction):
             return dict(mean=m_, lq=lo, uq=hi)
         return dict(mean=m_.cpu().numpy(), lq=lo.cpu().numpy(), uq=hi.cpu().numpy())
 
+    def get_y_error_stats(self, y_test, quantile=0.025, noise=None, mape_floor=None, fields=False):
+        """Extension: the test-error table of assess_all_models.py:523-552 for this object's designs in one
+        streaming pass -- reconstruction, mean / quantiles over samples and the comparison with the test fields are fused, so
+        neither the per-sample fields nor (unless `fields`) the mean / limit fields are written to memory.
+        y_test (npred, n_y) in native units; `noise` as in get_y_stats; `mape_floor`: outputs below it are left out of the
+        MAPE (the reference uses the 10 % quantile of its whole test matrix; default: that quantile of `y_test`).
+        Returns dict(rmse, mape, lq, uq, frac_covered (each (npred,)), integrated_ci, mape_floor[, mean, lq_field, uq_field])."""
+        sd = self.model.data.sim_data
+        if self.model.data.scalar_out:
+            raise NotImplementedError('get_y_error_stats is for multivariate (K basis) models')
+        torch = _lib.require_cuda()
+        yt = y_test if torch.is_tensor(y_test) else torch.as_tensor(np.ascontiguousarray(np.asarray(y_test, dtype=np.float32)))
+        yt = yt.to(device='cuda', dtype=torch.float32)
+        if mape_floor is None:
+            # np.quantile(y_test, 0.1): linear interpolation between the two neighbouring order statistics
+            flat = yt.reshape(-1)
+            pos = 0.1 * (flat.numel() - 1)
+            k0 = int(np.floor(pos))
+            lo_v = torch.kthvalue(flat, k0 + 1).values
+            hi_v = torch.kthvalue(flat, min(k0 + 2, flat.numel())).values
+            mape_floor = float(lo_v + (hi_v - lo_v) * (pos - k0))
+        sdd, mud = sd.stats_device()
+        err, fl = ops.reconstruct_errstats(np.asarray(self.w, dtype=np.float32), self._basis_device(), sdd, mud, yt,
+                                           mape_floor, q=quantile, noise=noise, want_fields=fields)
+        n_y = yt.shape[1]
+        out = dict(rmse=np.sqrt(err[:, 0] / n_y), mape=err[:, 1] / err[:, 2], lq=err[:, 4] / n_y, uq=err[:, 5] / n_y,
+                   frac_covered=err[:, 3] / n_y, integrated_ci=float(np.mean((err[:, 5] - err[:, 4]) / n_y)),
+                   mape_floor=mape_floor)
+        if fields:
+            out.update(mean=fl[0], lq_field=fl[1], uq_field=fl[2])
+        return out
+
 
 class SepiaXvalEmulatorPrediction:
     """Imported, never called, by the reference (assess_all_models.py:31-32)."""

@@ -160,6 +160,18 @@ int ggp_reconstruct_stats_f32(const float* w, const float* K, const float* sd, i
                               int mean_len, const float* noise, int nsamp, int npred, int pu, long long n_y, double q,
                               float* ymean_out, float* ylo_out, float* yhi_out, void* stream);
 
+/* Same pass with the test-error statistics of assess_all_models.py:523-538 fused in: for every test design t
+ *   err[t] = { sum (ymean - y_test)^2,  sum |ymean - y_test| / y_test over y_test >= mape_floor,  count(y_test >= mape_floor),
+ *              count(ylo <= y_test <= yhi),  sum ylo,  sum yhi }        (FP64 sums over the n_y outputs, fixed order)
+ * from which RMSE, MAPE (the reference masks y_test below its 10 % quantile: mape_floor), coverage, mean limits and the
+ * integrated interval width follow.  ymean_out / ylo_out / yhi_out may all be null: then no field is written at all.
+ * y_test[npred][n_y]; err_out[npred][6]; workspace: ggp_errstats_workspace_bytes(npred, n_y). */
+long long ggp_errstats_workspace_bytes(int npred, long long n_y);
+int ggp_reconstruct_errstats_f32(const float* w, const float* K, const float* sd, int sd_len, const float* mean,
+                                 int mean_len, const float* noise, int nsamp, int npred, int pu, long long n_y, double q,
+                                 const float* y_test, float mape_floor, float* ymean_out, float* ylo_out, float* yhi_out,
+                                 double* err_out, void* workspace, long long workspace_bytes, void* stream);
+
 /* ---- Sobol' / Saltelli sensitivity statistics --------------------------------
  * src/utils.py:80-92 (point estimates), :97-118 and :213-243 (the statistics scipy.stats.bootstrap evaluates 9999 times and
  * the BCa jackknife N times; callers sensitivity_indices.py:96,214).  For each of R index sets ids (n entries of 0..N-1;

@@ -119,3 +119,63 @@ def test_fused_stats_match_numpy_postprocessing(cuda, nsamp, npred, n_y, q):
     np.testing.assert_allclose(m_, ref_mean, rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(lo, ref_lo, rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(hi, ref_hi, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('nsamp,npred,n_y,q', [(64, 4, 3001, 0.025), (128, 2, 1500, 0.025), (16, 5, 2048, 0.05)])
+def test_fused_error_statistics_match_assess_all_models(cuda, nsamp, npred, n_y, q):
+    """assess_all_models.py:489-538 in one pass (ggp_reconstruct_errstats_f32): RMSE, MAPE above the 10 % quantile of the test
+    matrix, coverage, mean limits, integrated interval width.  The reference works in float32 (ypreds, np.mean, np.quantile on
+    float32 arrays); the kernel forms float32 fields and sums in FP64: tolerance 2e-5 relative, coverage within the few outputs
+    whose limit lies within float32 round-off of the test value."""
+    from gladsgp_b200 import ops
+    from oracle import assess_oracle as ao
+    rng = np.random.default_rng(11)
+    pu = 10
+    w = rng.standard_normal((nsamp, npred, pu)).astype(np.float32)
+    K = rng.standard_normal((pu, n_y)).astype(np.float32)
+    sd = rng.uniform(0.1, 0.3, n_y).astype(np.float32); mu = (2.0 + rng.standard_normal(n_y) * 0.2).astype(np.float32)
+    noise = (rng.standard_normal((nsamp, npred)) / np.sqrt(rng.uniform(20, 200, (nsamp, 1)))).astype(np.float32)
+    ym, ylq, yuq = ao.fields(w, K, sd, mu, noise, q)
+    y_test = (ym + 0.4 * rng.standard_normal(ym.shape) * sd).astype(np.float32)
+    ref = ao.error_statistics(ym, ylq, yuq, y_test)
+    err, fl = ops.reconstruct_errstats(w, K, sd, mu, y_test, float(ref['mape_floor']), q=q, noise=noise, want_fields=True)
+    np.testing.assert_allclose(np.sqrt(err[:, 0] / n_y), ref['rmse'], rtol=2e-5)
+    np.testing.assert_allclose(err[:, 1] / err[:, 2], ref['mape'], rtol=2e-5)
+    np.testing.assert_allclose(err[:, 4] / n_y, ref['lq'], rtol=2e-5)
+    np.testing.assert_allclose(err[:, 5] / n_y, ref['uq'], rtol=2e-5)
+    assert np.all(np.abs(err[:, 3] - ref['frac_covered'] * n_y) <= 3)
+    assert np.array_equal(err[:, 2], np.sum(y_test >= ref['mape_floor'], axis=1))
+    np.testing.assert_allclose(np.mean((err[:, 5] - err[:, 4]) / n_y), ref['integrated_ci'], rtol=2e-5)
+    # fields, when asked for, are those of reconstruct_stats; without them the sums are identical (and deterministic)
+    m_, lo, hi = [t.cpu().numpy() for t in ops.reconstruct_stats(w, K, sd, mu, q=q, noise=noise)]
+    assert np.array_equal(fl[0].cpu().numpy(), m_) and np.array_equal(fl[1].cpu().numpy(), lo) and np.array_equal(fl[2].cpu().numpy(), hi)
+    err2, none = ops.reconstruct_errstats(w, K, sd, mu, y_test, float(ref['mape_floor']), q=q, noise=noise)
+    assert none is None and np.array_equal(err, err2)
+
+
+def test_get_y_error_stats_api(cuda):
+    """SepiaEmulatorPrediction.get_y_error_stats: default MAPE floor = np.quantile(y_test, 0.1)."""
+    from oracle import assess_oracle as ao
+    from sepia.SepiaData import SepiaData
+    from sepia.SepiaModel import SepiaModel
+    from sepia.SepiaPredict import SepiaEmulatorPrediction
+    pr = make_problem(m=64, q=3, pu=2, n_x=40, n_t=30)
+    data = SepiaData(t_sim=pr['t'], y_sim=pr['y'], y_ind_sim=np.arange(pr['y'].shape[1], dtype=float))
+    data.transform_xt(t_notrans=np.arange(3)); data.standardize_y(y_mean=pr['mu'], y_sd=pr['sd']); data.create_K_basis(K=pr['K'])
+    model = SepiaModel(data)
+    samples = synthetic.posterior_samples(64, model.num.p + model.num.q, 2, seed=4)
+    tp = synthetic.test_design(4, 3)
+    np.random.seed(0)
+    pe = SepiaEmulatorPrediction(t_pred=tp, samples=samples, model=model)
+    pe.w = pe.w.astype(np.float32)
+    rng = np.random.default_rng(1)
+    noise = (rng.standard_normal((64, 4)) / np.sqrt(np.asarray(samples['lamWOs'], dtype=np.float64).reshape(-1, 1))).astype(np.float32)
+    y_test = (pe.get_y().mean(axis=0) + 0.05 * rng.standard_normal((4, pr['y'].shape[1]))).astype(np.float32)
+    got = pe.get_y_error_stats(y_test, quantile=0.025, noise=noise)
+    ym, ylq, yuq = ao.fields(pe.w, pr['K'], np.asarray(pr['sd'], dtype=np.float32), np.asarray(pr['mu'], dtype=np.float32), noise, 0.025)
+    ref = ao.error_statistics(ym, ylq, yuq, y_test)
+    assert abs(got['mape_floor'] - ref['mape_floor']) <= 1e-6 * abs(ref['mape_floor'])
+    for k in ('rmse', 'mape', 'lq', 'uq'):
+        np.testing.assert_allclose(got[k], ref[k], rtol=5e-5, err_msg=k)
+    assert np.all(np.abs(got['frac_covered'] - ref['frac_covered']) <= 4.0 / y_test.shape[1])
+    assert abs(got['integrated_ci'] - ref['integrated_ci']) <= 5e-5 * abs(ref['integrated_ci'])

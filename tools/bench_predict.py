@@ -58,6 +58,10 @@ def main():
     tst = ev(lambda: ops.reconstruct_stats(w3, K, sd, mu, q=0.025, noise=nz), iters=5, warm=2)
     res['stats_ms_64x4'] = tst
     res['stats_equiv_materialised_gbs'] = 4.0 * ns_ * np_ * n_y / tst / 1e6
+    # the same pass with the test-error sums fused in and no field written (assess_all_models.py:523-538)
+    yt = torch.randn(np_, n_y, device='cuda') + 2.0
+    tes = ev(lambda: ops.reconstruct_errstats(w3, K, sd, mu, yt, 1.0, q=0.025, noise=nz), iters=5, warm=2)
+    res['errstats_ms_64x4'] = tes
     del out, K
     # rSVD passes on a 512 x 1.46M float32 ensemble
     Xe = torch.randn(m, n_y, device='cuda')
