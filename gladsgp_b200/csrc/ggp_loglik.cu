@@ -9,26 +9,32 @@ namespace ggp {
 // ---------------------------------------------------------------------------------------------
 // (1) product squared-exponential covariance, materialised (SepiaDistCov type 1).
 // 8*m*m bytes written per matrix.  One CTA per (64x64 tile pair, matrix): the tile (bi >= bj) is
-// computed once (half the exps; 4x4 distances per thread in registers, in-kernel exp) and written
-// twice -- directly and transposed through shared memory, both as 16-byte streaming stores.
-// Measured 2.8 TB/s: the double-precision exponential, not HBM, is the bound (profiles/r1_cov_build_summary.txt).
+// computed once (half the exps) and written twice -- directly and transposed -- as 16-byte streaming stores.
+// Distances are the rank-(d+2) DMMA product of pair_cov (ggp_chol.cuh): warp w owns the 8 rows 8w..8w+7 of the tile,
+// 3 DMMA steps per 8x8 block at d = 9; the 16 exponentials of a lane are inlined; the tile goes through shared memory
+// so that both copies leave as full 128-byte lines.
 // ---------------------------------------------------------------------------------------------
 constexpr int CT = 64;
+constexpr int CT_LD = CT + 1;
 
+// KSC: compile-time number of DMMA steps of the distance product (0 = runtime), so that the fragment addresses are constants
+template <int KSC>
 __global__ void __launch_bounds__(256, 4)
 cov_build_kernel(const double* __restrict__ X, int m, int d, const double* __restrict__ beta,
                  const double* __restrict__ lamz, const double* __restrict__ diag_add,
                  double* __restrict__ C, int ntile)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* Sr = reinterpret_cast<double*>(smem_raw);      // [d][CT] scaled row coordinates (transposed)
-    double* Sc = Sr + CT * d;                              // [d][CT] scaled column coordinates
-    double* T = Sc + CT * d;                               // [CT][CT+1] transposed tile
-    double* etab = T + CT * (CT + 1);                      // [32]
+    const int KS = KSC > 0 ? KSC : cov_ksteps(d), K4 = 4 * KS;
+    double* XA = reinterpret_cast<double*>(smem_raw);      // [CT][K4] row side:    [x~, |x~|^2, 1, 0..]
+    double* XB = XA + CT * K4;                             // [CT][K4] column side: [2 x~, -1, -|x~|^2, 0..]
+    double* T = XB + CT * K4;                              // [CT][CT_LD] the tile
+    double* etab = T + CT * CT_LD;                         // [32]
+    double* sbs = etab + 32;                               // [d] sqrt(beta)
     const int b = blockIdx.y;
     // decode lower-triangular tile index
     int t = blockIdx.x;
-    int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
     while (bi * (bi + 1) / 2 > t) --bi;
     const int bj = t - bi * (bi + 1) / 2;
@@ -36,76 +42,93 @@ cov_build_kernel(const double* __restrict__ X, int m, int d, const double* __res
     const double il = 1.0 / lamz[b];
     const double dg = il + diag_add[b];
     const int r0 = bi * CT, c0 = bj * CT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     fill_exp_table(etab);
-    for (int idx = threadIdx.x; idx < CT * d; idx += blockDim.x) {
-        const int k = idx / CT, r = idx - k * CT;
-        const double sb = sqrt(be[k]);
-        Sr[idx] = (r0 + r < m) ? X[(size_t)(r0 + r) * d + k] * sb : 0.0;
-        Sc[idx] = (c0 + r < m) ? X[(size_t)(c0 + r) * d + k] * sb : 0.0;
+    if (tid >= 128 && tid < 128 + d) sbs[tid - 128] = sqrt(be[tid - 128]);
+    __syncthreads();
+    if (tid < 2 * CT) {
+        // thread per point: rows of the tile (tid < CT) and columns (tid >= CT)
+        const bool colside = tid >= CT;
+        const int lr = colside ? tid - CT : tid;
+        const int pt = (colside ? c0 : r0) + lr;
+        double* dst = (colside ? XB : XA) + lr * K4;
+        double rr = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double x = (pt < m) ? __ldg(X + (size_t)pt * d + k) * sbs[k] : 0.0;
+            rr = fma(x, x, rr);
+            dst[k] = colside ? 2.0 * x : x;
+        }
+        for (int k = d; k < K4; ++k) dst[k] = 0.0;
+        if (pt < m) {
+            dst[d] = colside ? -1.0 : rr;
+            dst[d + 1] = colside ? -rr : 1.0;
+        }
+    }
+    __syncthreads();
+    // -dist for the warp's 8 rows x 64 columns
+    double dn[8][2];
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) { dn[cb][0] = 0.0; dn[cb][1] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+        const double a = XA[(8 * warp + g) * K4 + 4 * s + q];
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) dmma884(dn[cb][0], dn[cb][1], a, XB[(8 * cb + g) * K4 + 4 * s + q]);
+    }
+    {
+        const int lr = 8 * warp + g;
+        double* trow = T + lr * CT_LD + 2 * q;
+        const int dcol = r0 + lr - c0 - 2 * q;               // tile-local column (minus 2q) of the diagonal entry, if any
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double v = exp_neg(dn[cb][e], etab) * il;
+                trow[8 * cb + e] = (dcol == 8 * cb + e) ? dg : v;
+            }
     }
     __syncthreads();
     double* Cb = C + (size_t)b * m * m;
     const bool vec2 = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    // each thread: 4 rows (ty + 16 i) x 4 consecutive columns (4 tx + j), distances in registers
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double dist[4][4];
+    const int cc = 2 * lane;
+    if (vec2 && r0 + CT <= m && c0 + CT <= m) {
+        // interior tile: no bounds checks.  8 rows x 64 columns per pass, a warp writes one 512-byte row segment
+        double* dst = Cb + (size_t)(r0 + warp) * m + c0 + cc;
+        const double* src = T + warp * CT_LD + cc;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int it = 0; it < 8; ++it)
+            __stcs(reinterpret_cast<double2*>(dst + (size_t)it * 8 * m), make_double2(src[it * 8 * CT_LD], src[it * 8 * CT_LD + 1]));
+        if (bi != bj) {
+            double* dt = Cb + (size_t)(c0 + warp) * m + r0 + cc;           // transposed copy: output row = column of the tile
+            const double* st = T + cc * CT_LD + warp;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dist[i][j] = 0.0;
-    for (int k = 0; k < d; ++k) {
-        double rv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rv[i] = Sr[k * CT + ty + 16 * i];
-        const double2 c01 = *reinterpret_cast<const double2*>(Sc + k * CT + 4 * tx);
-        const double2 c23 = *reinterpret_cast<const double2*>(Sc + k * CT + 4 * tx + 2);
-        const double cv[4] = {c01.x, c01.y, c23.x, c23.y};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double df = rv[i] - cv[j];
-                dist[i][j] = fma(df, df, dist[i][j]);
-            }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int lr = ty + 16 * i;
-        const int r = r0 + lr;
-        double v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int lc = 4 * tx + j;
-            v[j] = (r == c0 + lc) ? dg : exp_neg(-dist[i][j], etab) * il;
-            T[lc * (CT + 1) + lr] = v[j];
+            for (int it = 0; it < 8; ++it)
+                __stcs(reinterpret_cast<double2*>(dt + (size_t)it * 8 * m), make_double2(st[it * 8], st[it * 8 + CT_LD]));
         }
+        return;
+    }
+    for (int it = 0; it < 8; ++it) {
+        const int lr = it * 8 + warp;
+        const int r = r0 + lr, c = c0 + cc;
         if (r < m) {
-            const int c = c0 + 4 * tx;
-            if (vec2 && c + 3 < m) {
-                __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c), make_double2(v[0], v[1]));
-                __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c + 2), make_double2(v[2], v[3]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (c + j < m) Cb[(size_t)r * m + c + j] = v[j];
+            const double v0 = T[lr * CT_LD + cc], v1 = T[lr * CT_LD + cc + 1];
+            if (vec2 && c + 1 < m) __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c), make_double2(v0, v1));
+            else {
+                if (c < m) Cb[(size_t)r * m + c] = v0;
+                if (c + 1 < m) Cb[(size_t)r * m + c + 1] = v1;
             }
         }
     }
     if (bi != bj) {
-        __syncthreads();
-        for (int rr = 0; rr < 4; ++rr) {
-            const int lr = ty + 16 * rr;          // row of the transposed tile = column of the original
-            const int r = c0 + lr;
+        for (int it = 0; it < 8; ++it) {
+            const int lc = it * 8 + warp;                  // tile column -> output row
+            const int r = c0 + lc, c = r0 + cc;
             if (r < m) {
-                const int c = r0 + 4 * tx;
-                const double* tp = T + lr * (CT + 1) + 4 * tx;
-                if (vec2 && c + 3 < m) {
-                    __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c), make_double2(tp[0], tp[1]));
-                    __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c + 2), make_double2(tp[2], tp[3]));
-                } else {
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        if (c + cc < m) Cb[(size_t)r * m + c + cc] = tp[cc];
+                const double v0 = T[cc * CT_LD + lc], v1 = T[(cc + 1) * CT_LD + lc];
+                if (vec2 && c + 1 < m) __stcs(reinterpret_cast<double2*>(Cb + (size_t)r * m + c), make_double2(v0, v1));
+                else {
+                    if (c < m) Cb[(size_t)r * m + c] = v0;
+                    if (c + 1 < m) Cb[(size_t)r * m + c + 1] = v1;
                 }
             }
         }
@@ -222,12 +245,22 @@ int ggp_cov_build_f64(const double* X, int m, int d, const double* beta, const d
     cudaStream_t st = (cudaStream_t)stream;
     int nt = (m + CT - 1) / CT;
     int ntile = nt * (nt + 1) / 2;
-    size_t smem = (size_t)(2 * CT * d + CT * (CT + 1) + 32) * sizeof(double);
+    size_t smem = (size_t)(2 * CT * 4 * cov_ksteps(d) + CT * CT_LD + 32 + d) * sizeof(double);
     GGP_ARG(smem <= 200 * 1024, "d too large for cov_build");
-    GGP_CUDA(cudaFuncSetAttribute(cov_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cov_build_kernel<<<dim3(ntile, B), 256, smem, st>>>(X, m, d, beta, lamz, diag_add, C_out, ntile);
-    GGP_CUDA(cudaGetLastError());
-    return GGP_OK;
+    auto run = [&](auto kern) -> int {
+        GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3(ntile, B), 256, smem, st>>>(X, m, d, beta, lamz, diag_add, C_out, ntile);
+        GGP_CUDA(cudaGetLastError());
+        return GGP_OK;
+    };
+    switch (cov_ksteps(d)) {
+        case 1: return run(cov_build_kernel<1>);
+        case 2: return run(cov_build_kernel<2>);
+        case 3: return run(cov_build_kernel<3>);
+        case 4: return run(cov_build_kernel<4>);
+        case 5: return run(cov_build_kernel<5>);
+        default: return run(cov_build_kernel<0>);
+    }
 }
 
 int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, const double* beta,
