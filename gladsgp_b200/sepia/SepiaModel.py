@@ -216,7 +216,7 @@ class SepiaModel:
             k = min(chunk, nsteps - done)
             state = np.random.get_state()
             us = np.random.random_sample(2 * P * k * n_chains).reshape(n_chains, -1)
-            st = step if step.ndim == 1 else step[done:done + k]
+            st = step if step.ndim in (1, 3) else step[done:done + k]      # (P,), (1, n_chains, P) or a per-step schedule
             out = eng.run(k, st, uniforms=us, do_propMH=do_propMH, init_sigwl=init, record=True,
                           record_accept=record_accept)
             used = eng.to_host(out['consumed'], 'consumed')
@@ -281,7 +281,15 @@ class SepiaModel:
         return draws, lps
 
     # ------------------------------------------------------------------ step-size tuning
-    def tune_step_sizes(self, n_burn, n_levels, prog=True, diagnostics=False, update_vals=True, verbose=False):
+    def tune_step_sizes(self, n_burn, n_levels, prog=True, diagnostics=False, update_vals=True, verbose=False,
+                        parallel=False):
+        """SEPIA's step-size tuning (src/model.py:234): one chain cycles through the ladder of trial sizes,
+        n_burn visits per level, then a binomial-logit fit per element picks the size with acceptance 1/e.
+        parallel=True (extension): after the same 10 warm-up steps the n_levels trial sizes run as
+        n_levels simultaneous chains of n_burn steps from the warmed-up state (one batched device run, n_levels times
+        fewer sequential steps); the acceptance counts feed the same fit and the chain of the middle level hands its
+        final state back.  Chain l is bit for bit the chain a single run with trial size l and its slice of the
+        np.random stream would produce (tests/test_gpu_api.py)."""
         print('Starting tune_step_sizes...')
         print('Default step sizes:')
         for prm in self.params.mcmcList:
@@ -294,21 +302,30 @@ class SepiaModel:
         ex = np.linspace(-(n_levels - 1) / 2.0, (n_levels - 1) / 2.0, n_levels)
         ladder = tb['step'][None, :] * np.power(2.0, ex)[:, None]            # (n_levels, P)
         warm = 10
-        nsteps = warm + n_burn * n_levels
-        sched = np.empty((nsteps, P))
-        sched[:warm] = tb['step']
-        sched[warm:] = np.tile(ladder, (n_burn, 1))
         saved = [b.val.copy() for b in blocks]
         saved_lp = self.params.lp.val
         bar = _progress(n_burn, 'Step size tuning', prog)
-        draws, lps, acc = self._run(nsteps, sched, do_propMH=False, record_accept=True)
+        if parallel:
+            draws, lps, _ = self._run(warm, tb['step'], do_propMH=False)
+            self._store_state(draws[-1, 0, :])
+            draws, lps, acc = self._run(n_burn, ladder[None, :, :], do_propMH=False, n_chains=n_levels, record_accept=True)
+            mid = n_levels // 2
+            self._store_state(draws[-1, mid, :])
+            final_lp = float(lps[-1, mid])
+            acc = acc.astype(np.int64).sum(axis=0)                           # accepts per (level, element)
+        else:
+            nsteps = warm + n_burn * n_levels
+            sched = np.empty((nsteps, P))
+            sched[:warm] = tb['step']
+            sched[warm:] = np.tile(ladder, (n_burn, 1))
+            draws, lps, acc = self._run(nsteps, sched, do_propMH=False, record_accept=True)
+            self._store_state(draws[-1, 0, :])          # SEPIA copies the tuning chain's final values back
+            final_lp = float(lps[-1, 0])
+            acc = acc[warm:, 0, :].reshape(n_burn, n_levels, P).sum(axis=0)      # accepts per (level, element)
         if bar is not None:
             bar.update(n_burn)
             bar.close()
-        self._store_state(draws[-1, 0, :])          # SEPIA copies the tuning chain's final values back
         final_blocks = [b.val.copy() for b in blocks]
-        final_lp = float(lps[-1, 0])
-        acc = acc[warm:, 0, :].reshape(n_burn, n_levels, P).sum(axis=0)      # accepts per (level, element)
         target = np.log(1.0 / (np.exp(1.0) - 1.0))
         new_step = tb['step'].copy()
         for e in range(P):

@@ -190,6 +190,43 @@ def test_tune_step_sizes_matches_oracle(cuda):
         np.testing.assert_allclose(getattr(model.params, name).val, getattr(om, name).val, rtol=1e-7)
 
 
+def test_parallel_step_size_tuning_equals_one_chain_per_level(cuda):
+    """tune_step_sizes(parallel=True): the n_levels trial sizes run as simultaneous chains; level l's
+    acceptance record is, bit for bit, that of a single chain run with trial size l on its slice of the np.random stream,
+    so the selected step sizes are those of n_levels separate runs."""
+    import contextlib, io, copy
+    pr = make_problem(m=64, q=3, pu=2)
+    data, model = _build(pr, 3)
+    n_burn, n_levels = 12, 4
+    _, tb = model._get_engine(1)
+    P = tb['theta'].size
+    ladder = tb['step'][None, :] * np.power(2.0, np.linspace(-(n_levels - 1) / 2.0, (n_levels - 1) / 2.0, n_levels))[:, None]
+    # reference: warm-up, then one run per level from the warmed-up state with the matching slice of the stream
+    np.random.seed(21)
+    draws, lps, _ = model._run(10, tb['step'], do_propMH=False)
+    model._store_state(draws[-1, 0, :])
+    warmed = [b.val.copy() for b in model._blocks()[0]]
+    state = np.random.get_state()
+    acc_ref = []
+    for lvl in range(n_levels):
+        for b, v in zip(model._blocks()[0], warmed):
+            b.val = v.copy()
+        np.random.set_state(state)
+        np.random.random_sample(lvl * 2 * P * n_burn)
+        _, _, acc = model._run(n_burn, ladder[lvl], do_propMH=False, record_accept=True)
+        acc_ref.append(acc[:, 0, :].astype(np.int64).sum(axis=0))
+    acc_ref = np.array(acc_ref)
+    data2, model2 = _build(pr, 3)
+    np.random.seed(21)
+    with contextlib.redirect_stdout(io.StringIO()):
+        lad, acc = model2.tune_step_sizes(n_burn, n_levels, prog=False, diagnostics=True, parallel=True)
+    np.testing.assert_array_equal(lad, ladder)
+    np.testing.assert_array_equal(acc, acc_ref)
+    for name in ('betaU', 'lamUz', 'lamWs', 'lamWOs'):
+        stp = getattr(model2.params, name).mcmc.stepParam
+        assert np.all(np.isfinite(stp)) and np.all(stp > 0)
+
+
 def test_batched_chains_equal_independent_single_chains(cuda):
     """Chains are independent units: a batched run of 3 chains gives, bit for bit, the 3 chains
     obtained one at a time from the same per-chain uniform streams."""
