@@ -125,8 +125,11 @@ def test_compute_paths_fail_loudly_without_cuda():
     pr = make_problem(m=24, q=2, pu=2, n_x=6, n_t=5)
     from sepia.SepiaModel import SepiaModel
     model = SepiaModel(_data(pr, 2))
+    from gladsgp_b200 import sensitivity
     for fn in (lambda: model.do_mcmc(2, prog=False), lambda: model.logLik(), lambda: model.tune_step_sizes(2, 2),
-               lambda: svd.randomized_svd(pr['y_std'], 3, k=0)):
+               lambda: model.tune_step_sizes(2, 2, parallel=True),
+               lambda: svd.randomized_svd(pr['y_std'], 3, k=0),
+               lambda: sensitivity.saltelli_sensitivity_indices(lambda x: x[:, :1] + x[:, 1:2], 2, 3, n_resamples=9)):
         with pytest.raises(GgpError):
             fn()
 
