@@ -38,15 +38,12 @@ def _evaluate_blocks(func, n_dim, m, AB=None):
     if AB is None:
         AB = stats.qmc.Sobol(d=2 * n_dim).random_base2(m=int(m))
     AB = np.asarray(AB)
-    A = AB[:, n_dim:]
-    B = AB[:, :n_dim]
-    f_A = np.asarray(func(A), dtype=np.float64)
-    f_B = np.asarray(func(B), dtype=np.float64)
-    f_AB = np.zeros((n_dim, f_A.shape[0], f_A.shape[1]))
-    for ix in range(n_dim):
-        C = B.copy()
-        C[:, ix] = A[:, ix]
-        f_AB[ix] = func(C)
+    base_a, base_b = AB[:, n_dim:], AB[:, :n_dim]                       # src/utils.py:68-69
+    f_A = np.asarray(func(base_a), dtype=np.float64)
+    f_B = np.asarray(func(base_b), dtype=np.float64)
+    f_AB = np.empty((n_dim,) + f_A.shape)
+    for i in range(n_dim):                                              # B with column i taken from A (:76-80)
+        f_AB[i] = func(np.where((np.arange(n_dim) == i)[None, :], base_a, base_b))
     return f_A, f_B, f_AB
 
 

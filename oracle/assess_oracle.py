@@ -14,31 +14,21 @@ import numpy as np
 
 
 def fields(w, K, sd_y, mu_y, noise, quantile):
-    """w (nsamp, npred, pu) f32; K (pu, n_y) f32; noise (nsamp, npred) f32 -> ypred_mean, ypred_lq, ypred_uq (npred, n_y) f32."""
+    """w (nsamp, npred, pu) f32; K (pu, n_y) f32; noise (nsamp, npred) f32 -> mean, lower, upper fields (npred, n_y) f32.
+    get_y() in float32, one noise value per (sample, design) scaled by sd_y (:489-497), mean and quantiles over samples (:498-500)."""
     w = np.asarray(w, dtype=np.float32)
-    ypreds = (np.tensordot(w, np.asarray(K, dtype=np.float32), axes=[[2], [0]]) * sd_y + mu_y).astype(np.float32)   # get_y()
-    error_preds = np.zeros(ypreds.shape, dtype=np.float32)
-    for l_pred in range(ypreds.shape[1]):
-        for l_sample in range(ypreds.shape[0]):
-            error_preds[l_sample][l_pred] = sd_y * noise[l_sample, l_pred]                   # :493-497
-    ypred_mean = np.mean(ypreds, axis=0)                                                     # :498
-    ypred_lq = np.quantile(ypreds + error_preds, quantile, axis=0)                           # :499
-    ypred_uq = np.quantile(ypreds + error_preds, 1 - quantile, axis=0)                       # :500
-    return ypred_mean, ypred_lq, ypred_uq
+    y_s = (np.tensordot(w, np.asarray(K, dtype=np.float32), axes=[[2], [0]]) * sd_y + mu_y).astype(np.float32)
+    z_s = y_s + (np.asarray(noise, dtype=np.float32)[:, :, None] * np.asarray(sd_y, dtype=np.float32)[None, None, :]).astype(np.float32)
+    return np.mean(y_s, axis=0), np.quantile(z_s, quantile, axis=0), np.quantile(z_s, 1 - quantile, axis=0)
 
 
-def error_statistics(ypred_mean, ypred_lq, ypred_uq, y_test):
-    """assess_all_models.py:523-538 -> dict of per-design arrays (+ the scalar 10 % quantile and integrated width)."""
-    pred_resid = ypred_mean - y_test
-    pred_rmse = np.sqrt(np.mean(pred_resid ** 2, axis=1))
-    lq = np.quantile(y_test, 0.1)
-    inner_mape = np.abs(pred_resid / y_test)
-    inner_mape[y_test < lq] = np.nan
-    pred_mape = np.nanmean(inner_mape, axis=1)
-    is_covered = np.logical_and(y_test >= ypred_lq, y_test <= ypred_uq)
-    frac_covered = is_covered.sum(axis=1) / is_covered.shape[1]
-    pred_lq = np.mean(ypred_lq, axis=1)
-    pred_uq = np.mean(ypred_uq, axis=1)
-    integrated_ci = np.mean(ypred_uq - ypred_lq)          # mean over equal batches of the batch means of (uq - lq), :521,:537
-    return dict(rmse=pred_rmse, mape=pred_mape, lq=pred_lq, uq=pred_uq, frac_covered=frac_covered,
-                integrated_ci=integrated_ci, mape_floor=lq)
+def error_statistics(y_mean, y_lo, y_hi, y_test):
+    """Per-design error columns of performance_n{m}_p{p}.csv (:523-538) + the 10 % quantile used as MAPE floor and the
+    integrated interval width."""
+    resid = y_mean - y_test
+    floor = np.quantile(y_test, 0.1)
+    ape = np.where(y_test < floor, np.nan, np.abs(resid / y_test))
+    inside = (y_test >= y_lo) & (y_test <= y_hi)
+    return dict(rmse=np.sqrt(np.mean(resid ** 2, axis=1)), mape=np.nanmean(ape, axis=1), lq=np.mean(y_lo, axis=1),
+                uq=np.mean(y_hi, axis=1), frac_covered=inside.sum(axis=1) / inside.shape[1],
+                integrated_ci=np.mean(y_hi - y_lo), mape_floor=floor)

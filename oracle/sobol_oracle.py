@@ -25,58 +25,51 @@ def sobol_matrix(n_dim, m, seed=None):
 
 
 def evaluate_blocks(func, AB, n_dim):
-    """f_A, f_B, f_AB[ix] in the reference's call order (src/utils.py:70-80)."""
-    A = AB[:, n_dim:]
-    B = AB[:, :n_dim]
-    f_A = func(A)
-    f_B = func(B)
-    f_AB = np.zeros((n_dim, f_A.shape[0], f_A.shape[1]))
-    for ix in range(n_dim):
-        C = B.copy()
-        C[:, ix] = A[:, ix]
-        f_AB[ix] = func(C)
-    return f_A, f_B, f_AB
+    """Function values on the two base designs and on the n_dim "radial" designs (B with column i taken from A), in the
+    reference's call order A, B, AB_0, ... (src/utils.py:68-80).  Returns f_A, f_B (N, p) and f_AB (n_dim, N, p)."""
+    base_a, base_b = AB[:, n_dim:], AB[:, :n_dim]
+    f_A = func(base_a)
+    f_B = func(base_b)
+    mixed = []
+    for i in range(n_dim):
+        swap = np.arange(n_dim) == i
+        mixed.append(func(np.where(swap[None, :], base_a, base_b)))
+    return f_A, f_B, np.stack(mixed).astype(np.float64)
+
+
+def _saltelli_ratios(fa, fb, fab, clamp):
+    """Saltelli (2010) estimators on already gathered rows: fa, fb (n, p), fab (n_dim, n, p) -> first, total (p, n_dim).
+    Numerators: mean f_A (f_AB - f_B) and half the mean of (f_B - f_AB)^2; denominator: population variance of the 2n pooled
+    values of f_A and f_B (src/utils.py:81-92; clamped at zero inside the bootstrap statistics, :101, :113)."""
+    n = fa.shape[0]
+    num_first = (fa[None, :, :] * (fab - fb[None, :, :])).sum(axis=1) / n            # (n_dim, p)
+    num_total = ((fb[None, :, :] - fab) ** 2).sum(axis=1) / n * 0.5
+    if clamp:
+        num_first = np.maximum(num_first, 0.0)
+        num_total = np.maximum(num_total, 0.0)
+    pooled_var = np.var(np.stack([fa, fb]), axis=(0, 1))                               # (p,)
+    return (num_first / pooled_var).T, (num_total / pooled_var).T
 
 
 def point_estimates(f_A, f_B, f_AB):
-    """first_order, total_index (p, n_dim): src/utils.py:71-92."""
-    n_dim = f_AB.shape[0]
-    first_order = np.zeros((f_A.shape[1], n_dim))
-    total_index = np.zeros((f_A.shape[1], n_dim))
-    var = np.var([f_A, f_B], axis=(0, 1))
-    for ix in range(n_dim):
-        f_C = f_AB[ix]
-        V_i = np.mean(f_A * (f_C - f_B), axis=0)
-        E_i = 0.5 * np.mean((f_B - f_C) ** 2, axis=0)
-        first_order[:, ix] = V_i / var
-        total_index[:, ix] = E_i / var
-    return first_order, total_index
+    """first_order, total_index (p, n_dim) on the full sample, not clamped (src/utils.py:71-92)."""
+    return _saltelli_ratios(f_A, f_B, f_AB, clamp=False)
 
 
 def statistics(f_A, f_B, f_AB, pcvar=None):
-    """The closures handed to scipy.stats.bootstrap (src/utils.py:97-118, :213-243)."""
-    def first_order_statistic(arg):
-        f_A_ = f_A[arg, :]
-        f_B_ = f_B[arg, :]
-        f_AB_ = f_AB[:, arg, :]
-        V_ix = np.mean(f_A_ * (f_AB_ - f_B_), axis=(1,))
-        V_ix[V_ix < 0] = 0
-        var = np.var([f_A_, f_B_], axis=(0, 1))
-        return (V_ix / var).T
+    """The index-set statistics scipy.stats.bootstrap is given (src/utils.py:97-118; with the explained-variance weighted sums of
+    :237-243 when pcvar is given): callables of one argument, the array of row indices of a resample."""
+    def first(rows):
+        return _saltelli_ratios(f_A[rows], f_B[rows], f_AB[:, rows], clamp=True)[0]
 
-    def total_index_statistic(arg):
-        f_A_ = f_A[arg, :]
-        f_B_ = f_B[arg, :]
-        f_AB_ = f_AB[:, arg, :]
-        E_ix = 0.5 * np.mean((f_B_ - f_AB_) ** 2, axis=(1,))
-        E_ix[E_ix < 0] = 0
-        var = np.var([f_A_, f_B_], axis=(0, 1))
-        return (E_ix / var).T
+    def total(rows):
+        return _saltelli_ratios(f_A[rows], f_B[rows], f_AB[:, rows], clamp=True)[1]
 
-    out = {'first_order': first_order_statistic, 'total_index': total_index_statistic}
+    out = {'first_order': first, 'total_index': total}
     if pcvar is not None:
-        out['general_first_order'] = lambda arg: np.sum(first_order_statistic(arg) * np.vstack(pcvar), axis=0)
-        out['general_total_index'] = lambda arg: np.sum(total_index_statistic(arg) * np.vstack(pcvar), axis=0)
+        wts = np.asarray(pcvar, dtype=np.float64)[:, None]
+        out['general_first_order'] = lambda rows: (first(rows) * wts).sum(axis=0)
+        out['general_total_index'] = lambda rows: (total(rows) * wts).sum(axis=0)
     return out
 
 
