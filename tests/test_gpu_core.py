@@ -227,3 +227,29 @@ def test_lookahead_and_plain_schedules_agree_bitwise(cuda, monkeypatch, m, q, pu
         assert np.array_equal(infos[0], infos[1]) and np.all(infos[0] > 0)
     finally:
         h.ggp_set_lookahead(old)
+
+
+def test_lookahead_repeated_runs_are_bit_identical(cuda):
+    """The look-ahead schedule hands pairs to warps through a shared-memory counter and orders its phases with named barriers;
+    which warp takes which pair varies from run to run, the result must not (compute-sanitizer is not available on this
+    pool: a data race would show up here as run-to-run differences).  More matrices than one wave of CTAs, ragged size."""
+    from gladsgp_b200 import ops
+    import torch
+    pr = make_problem(m=257, q=4, pu=2)
+    num = pr['num']
+    B = 700
+    rng = np.random.default_rng(3)
+    beta = np.exp(rng.uniform(np.log(0.05), np.log(3.0), size=(B, num.d)))
+    lamz = rng.uniform(0.5, 2.0, B); dadd = rng.uniform(1e-3, 1e-2, B)
+    W = np.tile(num.w.T, (B // 2, 1))
+    Xd, Wd, bd, ld, dd = [torch.as_tensor(np.ascontiguousarray(a), device='cuda') for a in (num.zt, W, beta, lamz, dadd)]
+    ref = None
+    for rep in range(6):
+        out = ops.loglik_batched(Xd, Wd, bd, ld, dd, want_factor=True, want_u=True)
+        got = (out['loglik'].clone(), out['u'].clone(), out['factor'][:, :4096].clone())
+        if ref is None:
+            ref = got
+            assert torch.isfinite(ref[0]).all()
+        else:
+            for a, b in zip(ref, got):
+                assert torch.equal(a, b), rep
