@@ -194,7 +194,7 @@ def test_cluster_and_single_cta_variants_agree_bitwise(cuda, monkeypatch):
     assert np.all(bad['loglik'].cpu().numpy() == -np.inf) and np.all(bad['info'].cpu().numpy() > 0)
 
 
-@pytest.mark.parametrize('m,q,pu', [(32, 2, 1), (100, 8, 3), (257, 4, 2), (512, 8, 2)])
+@pytest.mark.parametrize('m,q,pu', [(32, 2, 1), (100, 8, 3), (257, 4, 2), (512, 8, 2), (1100, 16, 1), (2049, 12, 1)])
 def test_lookahead_and_plain_schedules_agree_bitwise(cuda, monkeypatch, m, q, pu):
     """The look-ahead schedule (diagonal block of panel j+1 factored while panel j is finished; dynamic pool of pairs)
     reorders work, not arithmetic: factor, u and log-likelihood equal the plain schedule and the cluster variant bit for bit."""
