@@ -7,8 +7,13 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-def test_gpu_matches_sepia_golden(cuda):
+@pytest.mark.parametrize('cluster', [None, '1', '4'])
+def test_gpu_matches_sepia_golden(cuda, monkeypatch, cluster):
+    """cluster None: the library's own choice (a thread-block cluster per matrix for this small batch); '1': one CTA per
+    matrix = the look-ahead schedule the large batches of the bench run; '4': 4-CTA clusters."""
     from gladsgp_b200 import ops
+    if cluster is not None:
+        monkeypatch.setenv('GGP_CLUSTER', cluster)
     g = np.load(os.path.join(GOLD, 'sepia_oracle.npz'))
     m = g['zt'].shape[0]
     js = g['js'].astype(int)
