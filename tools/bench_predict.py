@@ -3,6 +3,8 @@ import json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gladsgp_b200 import ops, synthetic, _lib
+if os.environ.get('GGP_LIB'):                      # developer A/B runs against a variant library
+    _lib.LIB_PATH = os.environ['GGP_LIB']
 
 
 def ev(fn, iters=3, warm=1):
