@@ -241,6 +241,116 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
     }
 }
 
+// ---- asynchronous copies (LDGSTS): global -> shared memory without a register stage ------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#ifndef GGP_DA
+#define GGP_DA 4          // depth (sub-slabs) of the per-warp shared-memory ring of A fragments; 0 = register ring (panel_gemm)
+#endif
+// per-warp scratch (doubles): covariance step (16 x 32) or the A ring of the product (DA slots x 2 units x 64)
+constexpr int SCR_DOUBLES = (GGP_DA * 128 > 512) ? GGP_DA * 128 : 512;
+constexpr int DA_SMALL = (GGP_DA > 4) ? 4 : GGP_DA;      // schedules whose scratch aliases LT + D (4 x 512 doubles)
+#ifndef GGP_BL1
+#define GGP_BL1 0         // 1: also pull the B lines of sub-slab s+2 k-blocks into L1 (pays only with a large L1 carve-out)
+#endif
+
+// Same product as panel_gemm (identical DMMA sequence per accumulator, hence bit-identical results), but the A
+// fragments travel global -> shared memory by cp.async (LDGSTS.128, L2 only) DA-1 sub-slabs ahead of their use instead
+// of one sub-slab ahead through registers: a warp no longer waits a full L2 / DRAM round trip per sub-slab, and the
+// loads in flight cost no registers.  The 16-byte piece a lane needs of an 8-row x 8-column unit block is piece number
+// `lane` of that block (row g, columns 2q..2q+1), so every lane copies exactly the pieces it later reads: no
+// cross-lane synchronisation, cp.async.wait_group alone orders the copy before the LDS.128 (conflict-free: consecutive
+// lanes, consecutive 16-byte pieces).  `ring`: per-warp shared memory, DA * NU * 64 doubles (the warp's covariance
+// scratch: idle during the product).  Packed-factor A operand only.
+template <int NU, int DA, int RB = GGP_RB>
+static __device__ __forceinline__ void panel_gemm_cp(double (&acc)[2][4][2], const double* __restrict__ Ap,
+                                                     const double* __restrict__ Lb, const int* __restrict__ soff, int j,
+                                                     int row0, const int (&rb)[2], int g, int q, double* __restrict__ ring)
+{
+    constexpr int PD = 2;                    // L2 prefetch distance in k-blocks (4 sub-slabs each)
+    static_assert(DA == 2 || DA == 4 || DA == 8, "ring depth 2, 4 or 8 sub-slabs");
+    static_assert(4 % RB == 0, "B ring depth must divide the 4 sub-slabs of a k-block");
+    const int lane = 4 * g + q;
+    const int nsub = 4 * j;
+    const int pa_unit = ((lane >> 4) < NU) ? (lane >> 4) : 0;
+    const int pa_ks = (lane >> 2) & 3;
+    const int pa_off = rb[pa_unit] * 8 + (lane & 3) * 16;
+#if GGP_BL1
+    const int pb_ks = lane >> 3;
+    const int pb_off = (row0 + 4 * (lane & 7)) * 8;
+#endif
+    int aoff[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) aoff[i] = (rb[i] + g) * 8 + 2 * q;
+    const int boff = (row0 + g) * 8 + 2 * q;
+    double* __restrict__ mine = ring + 2 * lane;              // this lane's piece; slot t, unit i at + (t * NU + i) * 64
+    double2 br[RB][4];
+    __syncwarp();                                             // previous user of the scratch (covariance step) is done
+#pragma unroll
+    for (int t = 0; t < DA - 1; ++t) {
+        if (t < nsub) {
+            const double* sl = Ap + soff[t];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) cp_async16(mine + (t * NU + i) * 64, sl + aoff[i]);
+        }
+        cp_async_commit();
+    }
+#pragma unroll
+    for (int t = 0; t < RB - 1; ++t)
+        if (t < nsub) {
+            const double* sl = Lb + soff[t] + boff;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) br[t][cb] = *reinterpret_cast<const double2*>(sl + 64 * cb);
+        }
+    for (int kb = 0; kb < j; ++kb) {
+        if (kb + PD < j) {
+            const int sp = 4 * (kb + PD);
+            prefetch_l2(Ap + soff[sp + pa_ks] + pa_off);
+#if GGP_BL1
+            const double* pb = Lb + soff[sp + pb_ks] + pb_off;
+            prefetch_l1(pb);
+            prefetch_l1(pb + 16);
+#endif
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int s = 4 * kb + ks;
+            if (s + DA - 1 < nsub) {
+                const double* sn = Ap + soff[s + DA - 1];
+                const int slot = (DA == 8) ? ((ks + 7) & 3) + 4 * ((kb + ((ks + 7) >> 2)) & 1) : (ks + DA - 1) % DA;
+#pragma unroll
+                for (int i = 0; i < NU; ++i) cp_async16(mine + (slot * NU + i) * 64, sn + aoff[i]);
+            }
+            cp_async_commit();
+            if (s + RB - 1 < nsub) {
+                const double* sbn = Lb + soff[s + RB - 1] + boff;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) br[(ks + RB - 1) % RB][cb] = *reinterpret_cast<const double2*>(sbn + 64 * cb);
+            }
+            cp_async_wait<DA - 1>();                          // sub-slab s has landed (the DA-1 younger groups may be in flight)
+            const int cur = (DA == 8) ? ks + 4 * (kb & 1) : ks % DA;
+            double2 a[NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) a[i] = *reinterpret_cast<const double2*>(mine + (cur * NU + i) * 64);
+            const double2 (&b)[4] = br[ks % RB];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                for (int i = 0; i < NU; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b[cb].x);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                for (int i = 0; i < NU; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b[cb].y);
+        }
+    }
+}
+
 // One 8-row unit: X = P * Minv^T on DMMA.  p[cb][e] (accumulator layout) doubles as the A fragment.
 static __device__ __forceinline__ void unit_trsm(const double (&p)[4][2], double (&x)[4][2],
                                                  const double* __restrict__ Minv, int g, int q)
@@ -271,17 +381,25 @@ static __device__ __forceinline__ void unit_trsm(const double (&p)[4][2], double
 
 // -dist for NU units x 32 panel columns: dn += [x~, |x~|^2, 1] . B.  KS > 0: compile-time step count (the row values
 // stay in registers: every global load of the pair is in flight before the first use); KS = 0: runtime loop.
+#ifndef GGP_XPRE
+#define GGP_XPRE 0        // 1: the row coordinates of a pair are loaded before its DMMA product (d <= 10) instead of after it
+#endif
+constexpr int XPRE_KS = 3;                   // steps covered by the early load (d + 2 <= 12)
+
 template <int NU, int KS>
 static __device__ __forceinline__ void cov_dist(double (&dn)[2][4][2], const double* const (&xr)[2],
                                                 const double* __restrict__ SCB, const double* __restrict__ sb,
-                                                int d, int q, int lane)
+                                                int d, int q, int lane, const double (*xpre)[XPRE_KS] = nullptr)
 {
     if constexpr (KS > 0) {
         double x[NU][KS];
 #pragma unroll
         for (int i = 0; i < NU; ++i)
 #pragma unroll
-            for (int s = 0; s < KS; ++s) x[i][s] = (4 * s + q < d) ? __ldg(xr[i] + 4 * s + q) : 0.0;
+            for (int s = 0; s < KS; ++s) {
+                if (KS <= XPRE_KS && xpre != nullptr) x[i][s] = xpre[i][s];
+                else x[i][s] = (4 * s + q < d) ? __ldg(xr[i] + 4 * s + q) : 0.0;
+            }
         double rn[NU];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
@@ -351,7 +469,8 @@ static __device__ __forceinline__ void pair_cov(double (&p)[2][4][2], const doub
                                                 const bool (&row_ok)[2], const double* __restrict__ SCB,
                                                 const double* __restrict__ sb, int d, int m, int row0, int q,
                                                 double inv_lamz, double diag, bool self,
-                                                const double* __restrict__ etab, double* __restrict__ scr, int lane)
+                                                const double* __restrict__ etab, double* __restrict__ scr, int lane,
+                                                const double (*xpre)[XPRE_KS] = nullptr)
 {
     double dn[2][4][2];
     const double* xr[2];
@@ -366,9 +485,9 @@ static __device__ __forceinline__ void pair_cov(double (&p)[2][4][2], const doub
     unsigned long long tla__ = clock64();
 #endif
     switch (ks) {       // d <= 18 (every configuration of the reference: d = 2 -> 1 step, 9 -> 3, 17 -> 5): register-resident form
-        case 1: cov_dist<NU, 1>(dn, xr, SCB, sb, d, q, lane); break;
-        case 2: cov_dist<NU, 2>(dn, xr, SCB, sb, d, q, lane); break;
-        case 3: cov_dist<NU, 3>(dn, xr, SCB, sb, d, q, lane); break;
+        case 1: cov_dist<NU, 1>(dn, xr, SCB, sb, d, q, lane, xpre); break;
+        case 2: cov_dist<NU, 2>(dn, xr, SCB, sb, d, q, lane, xpre); break;
+        case 3: cov_dist<NU, 3>(dn, xr, SCB, sb, d, q, lane, xpre); break;
         case 4: cov_dist<NU, 4>(dn, xr, SCB, sb, d, q, lane); break;
         case 5: cov_dist<NU, 5>(dn, xr, SCB, sb, d, q, lane); break;
         default: cov_dist<NU, 0>(dn, xr, SCB, sb, d, q, lane); break;
@@ -508,8 +627,13 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
             // ------------------------------------------------------------------ 1. DMMA update
             GGP_TICKW(2, 23, acc[0][0][0]);
             if (j > 0) {
+#if GGP_DA > 0
+                if (nu == 2) panel_gemm_cp<2, DA_SMALL>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, scr);
+                else if (nu == 1) panel_gemm_cp<1, DA_SMALL>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, scr);
+#else
                 if (nu == 2) panel_gemm<2, RA>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
                 else if (nu == 1) panel_gemm<1>(acc, Lp, Lp, sm.soff, j, row0, rb, g, q, 0);
+#endif
             }
             GGP_TICKW(2, 20, acc[0][0][0] + acc[1][3][1] + acc[0][3][1] + acc[1][0][0]);
             // ------------------------------------------------------------------ 2. covariance, P = C - S (registers)
@@ -748,7 +872,7 @@ struct LaSmem {
 
 __host__ __device__ inline size_t la_smem_bytes(int Mp, int d) {
     const int dpad = (d + 1) & ~1;
-    return (size_t)(32 * MI_LD + 32 * LT_LD + 32 * D_LD + 32 + 64 + 8 + 32 + Mp + dpad + 2 * sc_doubles(d) + NWARP * 512) * sizeof(double) +
+    return (size_t)(32 * MI_LD + 32 * LT_LD + 32 * D_LD + 32 + 64 + 8 + 32 + Mp + dpad + 2 * sc_doubles(d) + NWARP * SCR_DOUBLES) * sizeof(double) +
            16 + (size_t)(Mp / 8) * sizeof(int);
 }
 
@@ -766,7 +890,7 @@ __device__ inline LaSmem carve_la_smem(unsigned char* base, int Mp, int d) {
     s.wres = p;     p += Mp;
     s.sb = p;       p += dpad;
     s.SC = p;       p += 2 * sc_doubles(d);
-    s.scr = p;      p += NWARP * 512;
+    s.scr = p;      p += NWARP * SCR_DOUBLES;
     s.flag = reinterpret_cast<int*>(p);
     s.soff = s.flag + 4;
     s.scsz = sc_doubles(d);
@@ -778,13 +902,39 @@ __device__ __forceinline__ void bar_pair01() { asm volatile("bar.sync 1, 64;" ::
 __device__ __forceinline__ void bar01_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar01_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
+// Role rotation.  Warps are bound to the SM's four sub-partitions by their index (warp w -> sub-partition w % 4), and the
+// look-ahead schedule gives the warps of a CTA very different shares of the tensor work (role 0 factors the diagonal
+// blocks, roles 2 and 3 do little else than the DMMA product).  With the same role on the same sub-partition in every
+// resident CTA, the DMMA pipes of two sub-partitions queue while the other two idle.  Each CTA therefore takes a rotation
+// from a per-SM arrival counter: the CTAs resident on one SM get different rotations, and every sub-partition sees the
+// same mix of roles.  Roles only decide WHICH warp computes an entry, never how: results are unchanged.
+#ifndef GGP_ROT
+#define GGP_ROT 1
+#endif
+static __device__ unsigned g_role_rot[1024];
+__device__ __forceinline__ int cta_role_rotation()          // every thread of the CTA; contains a __syncthreads
+{
+#if GGP_ROT
+    __shared__ int rot_sm;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        rot_sm = (int)(atomicAdd(&g_role_rot[smid & 1023u], 1u) & (unsigned)(NWARP - 1));
+    }
+    __syncthreads();
+    return rot_sm;
+#else
+    return 0;
+#endif
+}
+
 static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, const double* __restrict__ X, int m, int Mp, int d,
                                     const double* beta, double lamz, double diag_add,
                                     const double* __restrict__ w, double* __restrict__ Lp,
-                                    double* __restrict__ u_out, int* info)
+                                    double* __restrict__ u_out, int* info, int rot = 0)
 {
-    static_assert(NWARP >= 2, "look-ahead variant needs at least two warps");
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    static_assert(NWARP >= 2 && (NWARP & (NWARP - 1)) == 0, "look-ahead variant needs a power-of-two number (>= 2) of warps");
+    const int tid = threadIdx.x, lane = tid & 31, warp = ((tid >> 5) + rot) & (NWARP - 1);     // warp = role
     const int g = lane >> 2, q = lane & 3;
     const int nP = Mp >> 5;
     const double inv_lamz = 1.0 / lamz;
@@ -792,7 +942,7 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
     double* __restrict__ D = sm.D;
     double* __restrict__ LT = sm.LT;
     double* __restrict__ wres = sm.wres;
-    double* __restrict__ scr = sm.scr + warp * 512;
+    double* __restrict__ scr = sm.scr + warp * SCR_DOUBLES;
 
     __syncthreads();   // previous user of the shared buffers is done
     if (tid < d) sm.sb[tid] = sqrt(beta[tid]);
@@ -891,9 +1041,27 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
             for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
+#if GGP_XPRE
+            // row coordinates of the pair for the covariance step: requested now, they arrive during the product
+            double xpre[2][XPRE_KS];
+            const bool use_xpre = cov_ksteps(d) <= XPRE_KS;
+            if (use_xpre) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = rb[i] + g;
+                    const double* xrow = X + (size_t)(r < m ? r : 0) * d;
+#pragma unroll
+                    for (int s2 = 0; s2 < XPRE_KS; ++s2) xpre[i][s2] = (4 * s2 + q < d) ? __ldg(xrow + 4 * s2 + q) : 0.0;
+                }
+            }
+#endif
             // ------------------------------------------------------------------ 1. DMMA update
             LA_TICK(2);
+#if GGP_DA > 0
+            if (cp > 0) panel_gemm_cp<2, GGP_DA>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, scr);
+#else
             if (cp > 0) panel_gemm<2>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, 0);
+#endif
 #ifdef GGP_PHASES
             if (acc[0][0][0] + acc[1][3][1] == 1.2345e300) tla__ = 0;
 #endif
@@ -902,7 +1070,12 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
             {
                 const int rr[2] = {rb[0] + g, rb[1] + g};
                 const bool ok[2] = {rr[0] < m, rr[1] < m};
+#if GGP_XPRE
+                pair_cov<2>(acc, X, rr, ok, sm.SC + (cp & 1) * sm.scsz, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane,
+                            use_xpre ? xpre : nullptr);
+#else
                 pair_cov<2>(acc, X, rr, ok, sm.SC + (cp & 1) * sm.scsz, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane);
+#endif
             }
 #ifdef GGP_PHASES
             if (acc[0][0][0] + acc[1][3][1] == 1.2345e300) tla__ = 0;

@@ -191,9 +191,10 @@ loglik_batched_kernel(const double* __restrict__ X, int m, int Mp, int d, const 
     double ll;
     if constexpr (LA) {
         LaSmem sm = carve_la_smem(smem_raw, Mp, d);
+        const int rot = cta_role_rotation();
         ll = eval_block_loglik_la(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],
                                   W + (size_t)b * w_stride, Lws + (size_t)b * l_stride,
-                                  u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr);
+                                  u_out ? u_out + (size_t)b * Mp : nullptr, info ? info + b : nullptr, rot);
     } else {
         EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
         ll = eval_block_loglik<CL, RA>(sm, X, m, Mp, d, beta + (size_t)b * d, lamz[b], diag_add[b],

@@ -1,16 +1,17 @@
 // Device-resident Metropolis-within-Gibbs sampler for the sim-only SEPIA model.
 //
 // Replaces SepiaModel.mcmc_step / do_mcmc / logPost (SURVEY.md 8a row a5, Appendix A.4-A.6,
-// A.10; driven from /root/reference/src/model.py:234-235).  One step is four launches:
-//   plan      (1 thread / chain)   draws every candidate of the step from the uniform stream
-//                                  (or copies them from replay tables): candidates, bounds and the
-//                                  PropMH correction depend only on start-of-step values.
-//   sweep     (1 CTA / (PC,chain)) the d betaU sites, lamUz and lamWs of one PC, sequentially;
-//                                  each site is one fused cov+Cholesky evaluation.  PCs are
-//                                  independent for these sites (log-lik is a sum of per-PC terms,
-//                                  priors are per element), so all PCs of all chains run at once.
-//   wos_eval  (1 CTA / (PC,chain)) per-PC terms under the candidate lamWOs
-//   finalize  (1 thread / chain)   lamWOs accept/reject, log-posterior, record the draw
+// A.10; driven from /root/reference/src/model.py:234-235).  One step is ONE launch:
+//   step kernel (1 CTA or cluster / (PC,chain)):
+//     sweep     the d betaU sites, lamUz and lamWs of one PC, sequentially; each site is one fused
+//               cov+Cholesky evaluation.  PCs are independent for these sites (the log-likelihood is a
+//               sum of per-PC terms, priors are per element), so all PCs of all chains run at once;
+//     lamWOs    the per-PC term under the candidate lamWOs (known since the start of the step);
+//     close     the last CTA of a chain to finish (per-chain arrival counter) sums the pu candidate terms in
+//               fixed order, accepts / rejects lamWOs, records the draw and the log-posterior, and draws
+//               the candidates of the NEXT step from the uniform stream (or copies them from the replay
+//               tables): candidates, bounds and the PropMH correction depend only on start-of-step values.
+//   plan kernel (1 thread / chain) runs once, before the first step.
 #include "ggp_chol.cuh"
 #include "../../include/gladsgp_b200.h"
 
@@ -43,10 +44,9 @@ struct Plan {
     int* valid;        // [n_chains][P]
 };
 
-__global__ void plan_kernel(ggp_mcmc_args a, Plan pl, int t)
+// candidates of step t for chain c (one thread)
+__device__ inline void plan_chain(const ggp_mcmc_args& a, const Plan& pl, int t, int c)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chains) return;
     const int P = a.d * a.pu + 2 * a.pu + 1;
     const double* th = a.theta + (size_t)c * P;
     const double* step = a.step + (size_t)t * a.step_stride_t + (size_t)c * a.step_stride_c;
@@ -98,6 +98,12 @@ __global__ void plan_kernel(ggp_mcmc_args a, Plan pl, int t)
     if (a.upos) a.upos[c] = pos;
 }
 
+__global__ void plan_kernel(ggp_mcmc_args a, Plan pl, int t)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < a.n_chains) plan_chain(a, pl, t, c);
+}
+
 // per-chain model data (per_chain_data != 0: chain c is its own model on the shared design)
 __device__ __forceinline__ const double* chain_w(const ggp_mcmc_args& a, int c, int j)
 {
@@ -128,24 +134,94 @@ __device__ inline void gather_block_params(const ggp_mcmc_args& a, const double*
     diag_add = 1.0 / (chain_lamsim(a, c, j) * lamwos) + 1.0 / lamws;
 }
 
+// Look-ahead variant: NOT inlined on purpose.  Inside the site loop of the step kernel the inlined body shared its register
+// budget with the loop's live state (a dozen pointers and indices) and spilled in the DMMA loops; as a function of its own
+// it gets the whole budget (the caller's few live values are saved once per evaluation), as in the batched log-likelihood
+// kernel.  (The cluster variant, 168 registers, has no spills when inlined and gets them as a function: it stays inline.)
+#ifndef GGP_EVAL_INLINE
+#define GGP_EVAL_INLINE 0
+#endif
+#if GGP_EVAL_INLINE
+#define GGP_EVAL_ATTR __forceinline__
+#else
+#define GGP_EVAL_ATTR __noinline__
+#endif
+static __device__ GGP_EVAL_ATTR double eval_la_call(unsigned char* smem_raw, const double* __restrict__ X, int m, int Mp, int d,
+                                                    const double* beta, double lamz, double diag_add,
+                                                    const double* __restrict__ w, double* __restrict__ Lp, int rot)
+{
+    LaSmem sm = carve_la_smem(smem_raw, Mp, d);
+    return eval_block_loglik_la(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr, rot);
+}
+
 // one evaluation by the CTA (cluster): CL = cluster variant, LA = look-ahead variant (one CTA per matrix)
 template <bool CL, bool LA, int RA>
 static __device__ __forceinline__ double eval_dispatch(unsigned char* smem_raw, const double* __restrict__ X, int m, int Mp, int d,
                                                        const double* beta, double lamz, double diag_add,
-                                                       const double* __restrict__ w, double* __restrict__ Lp)
+                                                       const double* __restrict__ w, double* __restrict__ Lp, int rot = 0)
 {
     if constexpr (LA) {
-        LaSmem sm = carve_la_smem(smem_raw, Mp, d);
-        return eval_block_loglik_la(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr);
+        return eval_la_call(smem_raw, X, m, Mp, d, beta, lamz, diag_add, w, Lp, rot);
     } else {
         EvalSmem sm = carve_eval_smem(smem_raw, Mp, d);
         return eval_block_loglik<CL, RA>(sm, X, m, Mp, d, beta, lamz, diag_add, w, Lp, nullptr, nullptr);
     }
 }
 
+// close of step t for chain c (one thread: the lead of the last CTA of the chain to arrive): lamWOs accept / reject from
+// the candidate terms summed in PC order, log-posterior, record.  Same arithmetic as SepiaModel.mcmc_step's last site.
+__device__ inline void finalize_chain(const ggp_mcmc_args& a, const Plan& pl, const double* __restrict__ sig_cand, int t, int c)
+{
+    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
+    double* th = a.theta + (size_t)c * P;
+    double* sig = a.sigwl + (size_t)c * pu;
+    const int s = P - 1;
+    const size_t o = (size_t)c * P + s;
+    int acc = 0;
+    if (pl.valid[o]) {
+        double sn = 0.0, so = 0.0;
+        for (int j = 0; j < pu; ++j) {
+            sn += sig_cand[(size_t)c * pu + j];
+            so += sig[j];
+        }
+        const double cand = pl.cand[o];
+        const size_t po = chain_prior_off(a, c) + s;
+        const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], cand) -
+                              elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], th[s]);
+        acc = pl.logu[o] < ((sn - so) + dprior) + pl.lacorr[o];
+        if (acc) {
+            th[s] = cand;
+            for (int j = 0; j < pu; ++j) sig[j] = sig_cand[(size_t)c * pu + j];
+        }
+    }
+    if (a.accepted) a.accepted[((size_t)t * a.n_chains + c) * P + s] = (unsigned char)acc;
+    // log posterior of the state at the end of the step: sum_j SigWl[j] + prior sums of the blocks in mcmcList
+    // (a block removed from mcmcList -- fixed flag 2 -- contributes nothing, as in SepiaModel.logPost)
+    if (a.lp_draws) {
+        double ll = 0.0;
+        for (int j = 0; j < pu; ++j) ll += sig[j];
+        double lpr = 0.0;
+        const int bounds[5] = {0, d * pu, d * pu + pu, d * pu + 2 * pu, P};
+        for (int blk = 0; blk < 4; ++blk) {
+            if (a.fixed[bounds[blk]] == 2) continue;
+            double sblk = 0.0;
+            for (int e = bounds[blk]; e < bounds[blk + 1]; ++e)
+                sblk += elem_log_prior(a.prior_kind[e], a.prior_a[chain_prior_off(a, c) + e], a.prior_b[chain_prior_off(a, c) + e], th[e]);
+            lpr += sblk;
+        }
+        a.lp_draws[(size_t)t * a.n_chains + c] = ll + lpr;
+    }
+    if (a.draws) {
+        double* dr = a.draws + ((size_t)t * a.n_chains + c) * P;
+        for (int e = 0; e < P; ++e) dr[e] = th[e];
+    }
+}
+
+// One mcmc_step of every chain in one launch (see the header of this file).
 template <bool CL, bool LA = false, int RA = GGP_RA>
 __global__ void __launch_bounds__(NT, CL ? GGP_CL_CTAS_PER_SM : GGP_CTAS_PER_SM)
-sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, int t)
+sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_stride, double* __restrict__ sig_cand,
+             unsigned* __restrict__ arrive, int t)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Mp = round_up32(a.m);
@@ -158,13 +234,16 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
     double* Lp = Lws + ((size_t)c * pu + j) * l_stride;
     const double* wj = chain_w(a, c, j);
     unsigned char* accd = a.accepted ? a.accepted + ((size_t)t * a.n_chains + c) * P : nullptr;
+    const int rot = LA ? cta_role_rotation() : 0;
 
-    for (int sl = 0; sl < d + 2; ++sl) {
-        const int s = (sl < d) ? j * d + sl : (sl == d ? d * pu + j : d * pu + pu + j);
+    // sites of PC j: d betaU elements, lamUz[j], lamWs[j]; then (sl == d + 2) the PC's term under the candidate lamWOs
+    for (int sl = 0; sl < d + 3; ++sl) {
+        const bool wos = (sl == d + 2);
+        const int s = wos ? P - 1 : ((sl < d) ? j * d + sl : (sl == d ? d * pu + j : d * pu + pu + j));
         const size_t o = (size_t)c * P + s;
         const int valid = pl.valid[o];
         if (!valid) {
-            if (lead && accd) accd[s] = 0;
+            if (lead && accd && !wos) accd[s] = 0;
             continue;
         }
         const double cand = pl.cand[o];
@@ -172,23 +251,39 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
         __syncthreads();
         gather_block_params(a, th, c, j, s, cand, beta_sm, lamz, diag_add);
         __syncthreads();
-        const double ll_new = eval_dispatch<CL, LA, RA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp);
+        const double ll_new = eval_dispatch<CL, LA, RA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, rot);
         if (lead) {
-            if (a.eval_count) atomicAdd(a.eval_count, 1ULL);
-            const double ll_old = sig[j];
-            const double xold = th[s];
-            const size_t po = chain_prior_off(a, c) + s;
-            const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], cand) -
-                                  elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], xold);
-            const bool acc = pl.logu[o] < ((ll_new - ll_old) + dprior) + pl.lacorr[o];
-            if (acc) {
-                th[s] = cand;
-                sig[j] = ll_new;
+            if (a.eval_count) atomicAdd(a.eval_count + (wos ? 1 : 0), 1ULL);
+            if (wos) {
+                sig_cand[(size_t)c * pu + j] = ll_new;
+            } else {
+                const double ll_old = sig[j];
+                const double xold = th[s];
+                const size_t po = chain_prior_off(a, c) + s;
+                const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], cand) -
+                                      elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], xold);
+                const bool acc = pl.logu[o] < ((ll_new - ll_old) + dprior) + pl.lacorr[o];
+                if (acc) {
+                    th[s] = cand;
+                    sig[j] = ll_new;
+                }
+                if (accd) accd[s] = acc ? 1 : 0;
             }
-            if (accd) accd[s] = acc ? 1 : 0;
         }
         if (CL) cluster_sync_all();        // the accepted state is visible to every CTA of the cluster
         else __syncthreads();
+    }
+    // close of the step: the last PC of the chain to arrive decides lamWOs, records, and plans the next step.  Its reads
+    // of the other PCs' results are ordered by the fence / atomic pair; the sums run in PC order whoever arrives last.
+    if (lead) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&arrive[c], 1u);
+        if (prev == (unsigned)pu - 1u) {
+            arrive[c] = 0u;
+            __threadfence();
+            finalize_chain(a, pl, sig_cand, t, c);
+            if (t + 1 < a.n_steps) plan_chain(a, pl, t + 1, c);
+        }
     }
 }
 
@@ -214,58 +309,14 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
         cand = pl.cand[o];
     }
     double lamz, diag_add;
+    const int rot = LA ? cta_role_rotation() : 0;
     gather_block_params(a, th, c, j, site, cand, beta_sm, lamz, diag_add);
     __syncthreads();
-    const double ll = eval_dispatch<CL, LA, RA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, chain_w(a, c, j), Lp);
+    const double ll = eval_dispatch<CL, LA, RA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, chain_w(a, c, j), Lp, rot);
     if (threadIdx.x == 0 && (!CL || cluster_ctarank() == 0)) {
         if (mode == 0) a.sigwl[(size_t)c * pu + j] = ll;
         else sig_cand[(size_t)c * pu + j] = ll;
         if (a.eval_count) atomicAdd(a.eval_count + 1, 1ULL);
-    }
-}
-
-__global__ void finalize_kernel(ggp_mcmc_args a, Plan pl, const double* __restrict__ sig_cand, int t)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chains) return;
-    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
-    double* th = a.theta + (size_t)c * P;
-    double* sig = a.sigwl + (size_t)c * pu;
-    const int s = P - 1;
-    const size_t o = (size_t)c * P + s;
-    int acc = 0;
-    if (pl.valid[o]) {
-        double sn = 0.0, so = 0.0;
-        for (int j = 0; j < pu; ++j) {
-            sn += sig_cand[(size_t)c * pu + j];
-            so += sig[j];
-        }
-        const double cand = pl.cand[o];
-        const size_t po = chain_prior_off(a, c) + s;
-        const double dprior = elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], cand) -
-                              elem_log_prior(a.prior_kind[s], a.prior_a[po], a.prior_b[po], th[s]);
-        acc = pl.logu[o] < ((sn - so) + dprior) + pl.lacorr[o];
-        if (acc) {
-            th[s] = cand;
-            for (int j = 0; j < pu; ++j) sig[j] = sig_cand[(size_t)c * pu + j];
-        }
-    }
-    if (a.accepted) a.accepted[((size_t)t * a.n_chains + c) * P + s] = (unsigned char)acc;
-    // log posterior of the state at the end of the step: sum_j SigWl[j] + block-wise prior sums
-    double ll = 0.0;
-    for (int j = 0; j < pu; ++j) ll += sig[j];
-    double lpr = 0.0;
-    const int bounds[5] = {0, d * pu, d * pu + pu, d * pu + 2 * pu, P};
-    for (int blk = 0; blk < 4; ++blk) {
-        double sblk = 0.0;
-        for (int e = bounds[blk]; e < bounds[blk + 1]; ++e)
-            sblk += elem_log_prior(a.prior_kind[e], a.prior_a[chain_prior_off(a, c) + e], a.prior_b[chain_prior_off(a, c) + e], th[e]);
-        lpr += sblk;
-    }
-    if (a.lp_draws) a.lp_draws[(size_t)t * a.n_chains + c] = ll + lpr;
-    if (a.draws) {
-        double* dr = a.draws + ((size_t)t * a.n_chains + c) * P;
-        for (int e = 0; e < P; ++e) dr[e] = th[e];
     }
 }
 
@@ -289,6 +340,7 @@ long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains)
     b += 3 * align256((size_t)n_chains * P * sizeof(double));                      // cand, lacorr, logu
     b += align256((size_t)n_chains * P * sizeof(int));                             // valid
     b += align256((size_t)n_chains * pu * sizeof(double));                         // sigwl_cand
+    b += align256((size_t)n_chains * sizeof(unsigned));                            // per-chain arrival counters
     return (long long)b;
 }
 
@@ -357,7 +409,8 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     pl.lacorr = reinterpret_cast<double*>(p); p += align256((size_t)a.n_chains * P * sizeof(double));
     pl.logu = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
     pl.valid = reinterpret_cast<int*>(p);     p += align256((size_t)a.n_chains * P * sizeof(int));
-    double* sig_cand = reinterpret_cast<double*>(p);
+    double* sig_cand = reinterpret_cast<double*>(p);  p += align256((size_t)a.n_chains * a.pu * sizeof(double));
+    unsigned* arrive = reinterpret_cast<unsigned*>(p);
     const long long l_stride = packed_doubles(Mp);
     const dim3 grid(a.pu * G, a.n_chains);
     const int cb = (a.n_chains + 31) / 32;
@@ -367,47 +420,45 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
                                : launch_maybe_cluster(eval_all_kernel<true, false, 2>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode);
         if (la) eval_all_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
         else eval_all_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
-        return cudaSuccess;
+        return cudaGetLastError();
     };
     auto launch_sweep = [&](int t) -> cudaError_t {
-        if (G > 1) return deep ? launch_maybe_cluster(sweep_kernel<true, false, 4>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, t)
-                               : launch_maybe_cluster(sweep_kernel<true, false, 2>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, t);
-        if (la) sweep_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
-        else sweep_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, t);
-        return cudaSuccess;
+        if (G > 1) return deep ? launch_maybe_cluster(sweep_kernel<true, false, 4>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, arrive, t)
+                               : launch_maybe_cluster(sweep_kernel<true, false, 2>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, arrive, t);
+        if (la) sweep_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, arrive, t);
+        else sweep_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, arrive, t);
+        return cudaGetLastError();
     };
-    if (a.init_sigwl) {
-        GGP_CUDA(launch_eval_all(0));
+    if (a.init_sigwl) GGP_CUDA(launch_eval_all(0));
+    if (a.n_steps > 0) {
+        GGP_CUDA(cudaMemsetAsync(arrive, 0, (size_t)a.n_chains * sizeof(unsigned), st));
+        plan_kernel<<<cb, 32, 0, st>>>(a, pl, 0);
         GGP_CUDA(cudaGetLastError());
     }
-    // optional per-kernel device timing (CUDA events on the launching stream)
+    // optional device timing of the step kernels (CUDA events on the launching stream)
     const bool timed = a.kernel_ms != nullptr && a.n_steps > 0;
     cudaEvent_t* ev = nullptr;
     if (timed) {
-        ev = new cudaEvent_t[3 * (size_t)a.n_steps];
-        for (int i = 0; i < 3 * a.n_steps; ++i) cudaEventCreate(&ev[i]);
+        ev = new cudaEvent_t[2 * (size_t)a.n_steps];
+        for (int i = 0; i < 2 * a.n_steps; ++i) cudaEventCreate(&ev[i]);
     }
-    for (int t = 0; t < a.n_steps; ++t) {
-        plan_kernel<<<cb, 32, 0, st>>>(a, pl, t);
-        if (timed) cudaEventRecord(ev[3 * t + 0], st);
-        launch_sweep(t);
-        if (timed) cudaEventRecord(ev[3 * t + 1], st);
-        launch_eval_all(1);
-        if (timed) cudaEventRecord(ev[3 * t + 2], st);
-        finalize_kernel<<<cb, 32, 0, st>>>(a, pl, sig_cand, t);
+    cudaError_t le = cudaSuccess;
+    for (int t = 0; t < a.n_steps && le == cudaSuccess; ++t) {
+        if (timed) cudaEventRecord(ev[2 * t + 0], st);
+        le = launch_sweep(t);
+        if (timed) cudaEventRecord(ev[2 * t + 1], st);
     }
-    cudaError_t le = cudaGetLastError();
     if (timed) {
         cudaStreamSynchronize(st);
-        double sw = 0.0, wo = 0.0;
-        for (int t = 0; t < a.n_steps; ++t) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[3 * t + 0], ev[3 * t + 1]); sw += ms;
-            cudaEventElapsedTime(&ms, ev[3 * t + 1], ev[3 * t + 2]); wo += ms;
-        }
-        a.kernel_ms[0] = sw;      // total sweep_kernel time (ms)
-        a.kernel_ms[1] = wo;      // total eval_all_kernel (lamWOs wave) time (ms)
-        for (int i = 0; i < 3 * a.n_steps; ++i) cudaEventDestroy(ev[i]);
+        double sw = 0.0;
+        if (le == cudaSuccess)
+            for (int t = 0; t < a.n_steps; ++t) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[2 * t + 0], ev[2 * t + 1]); sw += ms;
+            }
+        a.kernel_ms[0] = sw;      // total step-kernel time (ms): sweep + lamWOs terms + close of the step
+        a.kernel_ms[1] = 0.0;     // (the lamWOs wave was a launch of its own before version 2)
+        for (int i = 0; i < 2 * a.n_steps; ++i) cudaEventDestroy(ev[i]);
         delete[] ev;
     }
     if (le != cudaSuccess) return cuda_fail(le, "mcmc launches");

@@ -119,7 +119,7 @@ class McmcEngine:
         self.theta = torch.zeros((self.n_chains, self.P), dtype=torch.float64, device=dev)
         self.sigwl = torch.zeros((self.n_chains, self.pu), dtype=torch.float64, device=dev)
         self.upos = torch.zeros(self.n_chains, dtype=torch.int64, device=dev)
-        self.launches_per_step = 4
+        self.launches_per_step = 1          # one fused step kernel per mcmc_step (+ one plan kernel per run)
 
     def set_tables(self, tb):
         torch, dev = self.torch, 'cuda'

@@ -227,7 +227,7 @@ class SepiaModel:
             lps.append(eng.to_host(out['lp'], 'lp'))
             if record_accept:
                 accs.append(eng.to_host(out['accepted'], 'accepted'))
-            self.launches += (1 if init else 0) + 4 * k
+            self.launches += (1 if init else 0) + 1 + k          # [initial per-PC terms] + plan + one step kernel per step
             init = False
             done += k
             if prog is not None:
