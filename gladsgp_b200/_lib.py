@@ -29,6 +29,8 @@ class McmcArgs(C.Structure):
         ('draws', C.c_void_p), ('lp_draws', C.c_void_p), ('accepted', C.c_void_p),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
         ('eval_count', C.c_void_p), ('kernel_ms', C.c_void_p),
+        ('pc_begin', C.c_int), ('pc_count', C.c_int), ('step_index', C.c_int), ('reserved0', C.c_int),
+        ('xchg', C.c_void_p),
     ]
 
 
@@ -50,6 +52,8 @@ SIGNATURES = {
     'ggp_sizeof_mcmc_args': (_I, []),
     'ggp_mcmc_workspace_bytes': (_LL, [_I, _I, _I, _I]),
     'ggp_mcmc_run_f64': (_I, [C.POINTER(McmcArgs), _P]),
+    'ggp_mcmc_plan_f64': (_I, [C.POINTER(McmcArgs), _I, _P]),
+    'ggp_mcmc_close_f64': (_I, [C.POINTER(McmcArgs), _I, _I, _P]),
     'ggp_predict_workspace_bytes': (_LL, [_I, _I, _I]),
     'ggp_predict_f64': (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _LL, _P]),
     'ggp_pred_cov_f64': (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P]),

@@ -256,6 +256,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // per-warp scratch (doubles): covariance step (16 x 32) or the A ring of the product (DA slots x 2 units x 64)
 constexpr int SCR_DOUBLES = (GGP_DA * 128 > 512) ? GGP_DA * 128 : 512;
 constexpr int DA_SMALL = (GGP_DA > 4) ? 4 : GGP_DA;      // schedules whose scratch aliases LT + D (4 x 512 doubles)
+#ifndef GGP_PD
+#define GGP_PD 2
+#endif
 #ifndef GGP_BL1
 #define GGP_BL1 0         // 1: also pull the B lines of sub-slab s+2 k-blocks into L1 (pays only with a large L1 carve-out)
 #endif
@@ -273,7 +276,7 @@ static __device__ __forceinline__ void panel_gemm_cp(double (&acc)[2][4][2], con
                                                      const double* __restrict__ Lb, const int* __restrict__ soff, int j,
                                                      int row0, const int (&rb)[2], int g, int q, double* __restrict__ ring)
 {
-    constexpr int PD = 2;                    // L2 prefetch distance in k-blocks (4 sub-slabs each)
+    constexpr int PD = GGP_PD;               // L2 prefetch distance in k-blocks (4 sub-slabs each)
     static_assert(DA == 2 || DA == 4 || DA == 8, "ring depth 2, 4 or 8 sub-slabs");
     static_assert(4 % RB == 0, "B ring depth must divide the 4 sub-slabs of a k-block");
     const int lane = 4 * g + q;
@@ -911,6 +914,9 @@ __device__ __forceinline__ void bar01_wait(int id) { asm volatile("bar.sync %0, 
 #ifndef GGP_ROT
 #define GGP_ROT 1
 #endif
+#ifndef GGP_STAGGER_US
+#define GGP_STAGGER_US 0
+#endif
 static __device__ unsigned g_role_rot[1024];
 __device__ __forceinline__ int cta_role_rotation()          // every thread of the CTA; contains a __syncthreads
 {
@@ -920,6 +926,13 @@ __device__ __forceinline__ int cta_role_rotation()          // every thread of t
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         rot_sm = (int)(atomicAdd(&g_role_rot[smid & 1023u], 1u) & (unsigned)(NWARP - 1));
+#if GGP_STAGGER_US > 0
+        // developer experiment: start the CTAs resident on one SM a fraction of an evaluation apart
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long wait_ns = (unsigned long long)rot_sm * GGP_STAGGER_US * 1000ULL;
+        do { __nanosleep(2000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < wait_ns);
+#endif
     }
     __syncthreads();
     return rot_sm;

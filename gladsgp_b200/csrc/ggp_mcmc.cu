@@ -226,7 +226,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Mp = round_up32(a.m);
     __shared__ double beta_sm[64];
-    const int j = CL ? blockIdx.x / cluster_nctarank() : blockIdx.x, c = blockIdx.y;
+    const int j = a.pc_begin + (CL ? blockIdx.x / cluster_nctarank() : blockIdx.x), c = blockIdx.y;
     const bool lead = (threadIdx.x == 0) && (!CL || cluster_ctarank() == 0);    // the one thread that owns the state
     const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
     double* th = a.theta + (size_t)c * P;
@@ -235,6 +235,12 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
     const double* wj = chain_w(a, c, j);
     unsigned char* accd = a.accepted ? a.accepted + ((size_t)t * a.n_chains + c) * P : nullptr;
     const int rot = LA ? cta_role_rotation() : 0;
+    const bool shard = a.pc_count > 0;                         // PC shard: results leave through a.xchg, no close here
+    double* xrow = shard ? a.xchg + ((size_t)j * a.n_chains + c) * (2 * d + 6) : nullptr;
+    if (shard && lead) {
+        xrow[d + 3] = sig[j];                                  // no valid lamWOs candidate: the term is not used
+        for (int e = 0; e < d + 2; ++e) xrow[d + 4 + e] = 0.0;
+    }
 
     // sites of PC j: d betaU elements, lamUz[j], lamWs[j]; then (sl == d + 2) the PC's term under the candidate lamWOs
     for (int sl = 0; sl < d + 3; ++sl) {
@@ -268,6 +274,7 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
                     sig[j] = ll_new;
                 }
                 if (accd) accd[s] = acc ? 1 : 0;
+                if (shard) xrow[d + 4 + sl] = acc ? 1.0 : 0.0;
             }
         }
         if (CL) cluster_sync_all();        // the accepted state is visible to every CTA of the cluster
@@ -275,7 +282,13 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
     }
     // close of the step: the last PC of the chain to arrive decides lamWOs, records, and plans the next step.  Its reads
     // of the other PCs' results are ordered by the fence / atomic pair; the sums run in PC order whoever arrives last.
-    if (lead) {
+    if (lead && shard) {
+        for (int e = 0; e < d; ++e) xrow[e] = th[j * d + e];
+        xrow[d] = th[d * pu + j];
+        xrow[d + 1] = th[d * pu + pu + j];
+        xrow[d + 2] = sig[j];
+        if (pl.valid[(size_t)c * P + (P - 1)]) xrow[d + 3] = sig_cand[(size_t)c * pu + j];
+    } else if (lead) {
         __threadfence();
         const unsigned prev = atomicAdd(&arrive[c], 1u);
         if (prev == (unsigned)pu - 1u) {
@@ -320,7 +333,54 @@ eval_all_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_
     }
 }
 
+// PC-sharded stepping: close of step t on every rank from the gathered rows (one thread per chain)
+__global__ void close_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ sig_cand, int t, int plan_next)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chains) return;
+    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
+    double* th = a.theta + (size_t)c * P;
+    double* sig = a.sigwl + (size_t)c * pu;
+    unsigned char* accd = a.accepted ? a.accepted + ((size_t)t * a.n_chains + c) * P : nullptr;
+    for (int j = 0; j < pu; ++j) {
+        const double* row = a.xchg + ((size_t)j * a.n_chains + c) * (2 * d + 6);
+        for (int e = 0; e < d; ++e) th[j * d + e] = row[e];
+        th[d * pu + j] = row[d];
+        th[d * pu + pu + j] = row[d + 1];
+        sig[j] = row[d + 2];
+        sig_cand[(size_t)c * pu + j] = row[d + 3];
+        if (accd) {
+            for (int e = 0; e < d; ++e) accd[j * d + e] = (unsigned char)(row[d + 4 + e] != 0.0);
+            accd[d * pu + j] = (unsigned char)(row[d + 4 + d] != 0.0);
+            accd[d * pu + pu + j] = (unsigned char)(row[d + 4 + d + 1] != 0.0);
+        }
+    }
+    finalize_chain(a, pl, sig_cand, t, c);
+    if (plan_next) plan_chain(a, pl, t + 1, c);
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// workspace carve-up shared by the entry points
+struct McmcWs {
+    double* Lws; Plan pl; double* sig_cand; unsigned* arrive;
+};
+static McmcWs carve_ws(const ggp_mcmc_args& a)
+{
+    const int Mp = round_up32(a.m);
+    const size_t P = (size_t)a.d * a.pu + 2 * a.pu + 1;
+    McmcWs w;
+    unsigned char* p = reinterpret_cast<unsigned char*>(a.workspace);
+    w.Lws = reinterpret_cast<double*>(p);
+    p += align256((size_t)a.n_chains * a.pu * packed_doubles(Mp) * sizeof(double));
+    w.pl.cand = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
+    w.pl.lacorr = reinterpret_cast<double*>(p); p += align256((size_t)a.n_chains * P * sizeof(double));
+    w.pl.logu = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
+    w.pl.valid = reinterpret_cast<int*>(p);     p += align256((size_t)a.n_chains * P * sizeof(int));
+    w.sig_cand = reinterpret_cast<double*>(p);  p += align256((size_t)a.n_chains * a.pu * sizeof(double));
+    w.arrive = reinterpret_cast<unsigned*>(p);
+    return w;
+}
 
 }  // namespace ggp
 
@@ -353,6 +413,13 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     GGP_ARG(a.X && a.W && a.lamsim && a.theta && a.sigwl, "null model/state pointer");
     GGP_ARG(a.prior_kind && a.prior_a && a.prior_b && a.lo && a.hi && a.prop_kind && a.fixed && a.step, "null table pointer");
     GGP_ARG(a.workspace, "null workspace");
+    GGP_ARG(a.pc_count >= 0 && a.pc_begin >= 0 && a.pc_begin + a.pc_count <= a.pu, "PC shard out of range");
+    if (a.pc_count > 0) {
+        GGP_ARG(a.n_steps == 1 && a.xchg, "a PC shard runs one step per call and needs xchg");
+        GGP_ARG(a.step_index >= 0, "step_index must be >= 0");
+    } else {
+        GGP_ARG(a.pc_begin == 0, "pc_begin without pc_count");
+    }
     if (a.replay) GGP_ARG(a.r_cand && a.r_logacorr && a.r_logu && a.r_valid, "replay tables missing");
     else GGP_ARG(a.uniforms && a.upos && a.n_uniform > 0, "uniform stream missing");
     const long long need = ggp_mcmc_workspace_bytes(a.m, a.d, a.pu, a.n_chains);
@@ -360,7 +427,7 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         set_error("ggp_mcmc_run_f64: workspace too small (%lld < %lld)", (long long)a.workspace_bytes, need);
         return GGP_ERR_WORKSPACE;
     }
-    if (!a.replay) {
+    if (!a.replay && a.pc_count == 0) {
         const long long P = (long long)a.d * a.pu + 2 * a.pu + 1;
         GGP_ARG(a.n_uniform >= 2 * P * a.n_steps, "uniform stream shorter than 2*P*n_steps");
     }
@@ -400,26 +467,22 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         GGP_CUDA(cudaFuncSetAttribute(eval_all_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
     }
 
-    const size_t P = (size_t)a.d * a.pu + 2 * a.pu + 1;
-    unsigned char* p = reinterpret_cast<unsigned char*>(a.workspace);
-    double* Lws = reinterpret_cast<double*>(p);
-    p += align256((size_t)a.n_chains * a.pu * packed_doubles(Mp) * sizeof(double));
-    Plan pl;
-    pl.cand = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
-    pl.lacorr = reinterpret_cast<double*>(p); p += align256((size_t)a.n_chains * P * sizeof(double));
-    pl.logu = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
-    pl.valid = reinterpret_cast<int*>(p);     p += align256((size_t)a.n_chains * P * sizeof(int));
-    double* sig_cand = reinterpret_cast<double*>(p);  p += align256((size_t)a.n_chains * a.pu * sizeof(double));
-    unsigned* arrive = reinterpret_cast<unsigned*>(p);
+    const McmcWs wsp = carve_ws(a);
+    double* Lws = wsp.Lws;
+    Plan pl = wsp.pl;
+    double* sig_cand = wsp.sig_cand;
+    unsigned* arrive = wsp.arrive;
     const long long l_stride = packed_doubles(Mp);
-    const dim3 grid(a.pu * G, a.n_chains);
+    const bool shard = a.pc_count > 0;
+    const dim3 grid_all(a.pu * G, a.n_chains);
+    const dim3 grid((shard ? a.pc_count : a.pu) * G, a.n_chains);
     const int cb = (a.n_chains + 31) / 32;
 
     auto launch_eval_all = [&](int mode) -> cudaError_t {
-        if (G > 1) return deep ? launch_maybe_cluster(eval_all_kernel<true, false, 4>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode)
-                               : launch_maybe_cluster(eval_all_kernel<true, false, 2>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode);
-        if (la) eval_all_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
-        else eval_all_kernel<false><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
+        if (G > 1) return deep ? launch_maybe_cluster(eval_all_kernel<true, false, 4>, grid_all, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode)
+                               : launch_maybe_cluster(eval_all_kernel<true, false, 2>, grid_all, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, mode);
+        if (la) eval_all_kernel<false, true><<<grid_all, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
+        else eval_all_kernel<false><<<grid_all, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
         return cudaGetLastError();
     };
     auto launch_sweep = [&](int t) -> cudaError_t {
@@ -430,6 +493,11 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         return cudaGetLastError();
     };
     if (a.init_sigwl) GGP_CUDA(launch_eval_all(0));
+    if (shard) {
+        // one step of a PC shard: candidates come from ggp_mcmc_plan_f64 / ggp_mcmc_close_f64, the close is the caller's
+        GGP_CUDA(launch_sweep(a.step_index));
+        return GGP_OK;
+    }
     if (a.n_steps > 0) {
         GGP_CUDA(cudaMemsetAsync(arrive, 0, (size_t)a.n_chains * sizeof(unsigned), st));
         plan_kernel<<<cb, 32, 0, st>>>(a, pl, 0);
@@ -462,6 +530,42 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         delete[] ev;
     }
     if (le != cudaSuccess) return cuda_fail(le, "mcmc launches");
+    return GGP_OK;
+}
+
+static int check_shard_args(const ggp_mcmc_args* args)
+{
+    GGP_ARG(args, "null args");
+    const ggp_mcmc_args& a = *args;
+    GGP_ARG(a.m > 0 && a.d > 0 && a.pu > 0 && a.n_chains > 0, "sizes must be positive");
+    GGP_ARG(a.theta && a.sigwl && a.workspace && a.fixed && a.step, "null state / table pointer");
+    GGP_ARG((long long)a.workspace_bytes >= ggp_mcmc_workspace_bytes(a.m, a.d, a.pu, a.n_chains), "workspace too small");
+    if (a.replay) GGP_ARG(a.r_cand && a.r_logacorr && a.r_logu && a.r_valid, "replay tables missing");
+    else GGP_ARG(a.uniforms && a.upos && a.n_uniform > 0, "uniform stream missing");
+    return GGP_OK;
+}
+
+int ggp_mcmc_plan_f64(const ggp_mcmc_args* args, int t, void* stream)
+{
+    const int rc = check_shard_args(args);
+    if (rc != GGP_OK) return rc;
+    const ggp_mcmc_args a = *args;
+    GGP_ARG(t >= 0, "t must be >= 0");
+    const McmcWs w = carve_ws(a);
+    plan_kernel<<<(a.n_chains + 31) / 32, 32, 0, (cudaStream_t)stream>>>(a, w.pl, t);
+    GGP_CUDA(cudaGetLastError());
+    return GGP_OK;
+}
+
+int ggp_mcmc_close_f64(const ggp_mcmc_args* args, int t, int plan_next, void* stream)
+{
+    const int rc = check_shard_args(args);
+    if (rc != GGP_OK) return rc;
+    const ggp_mcmc_args a = *args;
+    GGP_ARG(t >= 0 && a.xchg, "t must be >= 0 and xchg non-null");
+    const McmcWs w = carve_ws(a);
+    close_kernel<<<(a.n_chains + 31) / 32, 32, 0, (cudaStream_t)stream>>>(a, w.pl, w.sig_cand, t, plan_next);
+    GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }
 

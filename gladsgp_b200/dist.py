@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU, independent units sharded across ranks, one gather.
 
 The path shards by independent unit: MCMC chains (no exchange until the draws are
-collected) and test-design blocks for prediction (one all_gather of per-shard moments).  NCCL on
-GPUs, gloo in the CPU tests.
+collected), the PCs of one chain (one all_gather of per-PC result rows per step: mcmc_by_pc), test-design
+blocks for prediction (one all_gather of per-shard moments) and output-column slabs of the ensemble for the
+rSVD.  NCCL on GPUs, gloo in the CPU tests.
 """
 import numpy as np
 
@@ -96,3 +97,43 @@ def randomized_svd_sharded(X_slab, p, k=None, q=1, omega_slab=None, products=Non
     U = (Q.double() @ E).float()
     Vh = ((E.T @ B) / S.clamp_min(1e-300)[:, None]).float()
     return U[:, :p], S[:p].float(), Vh[:p]
+
+
+# ---------------------------------------------------------------------------------------------
+# one chain, PCs spread over the ranks (SURVEY.md 8e ii; BASELINE.json north_star "by independent PC component")
+# ---------------------------------------------------------------------------------------------
+def pc_shard(pu, rank, world):
+    """PCs [begin, begin + count) swept by `rank`: equal blocks of ceil(pu / world) (the last ranks may own fewer or
+    none), so that a rank's rows form one contiguous, equally sized slot of the exchange buffer."""
+    cp = -(-int(pu) // int(world))
+    lo = min(pu, rank * cp)
+    return lo, min(pu, lo + cp) - lo, cp
+
+
+class PcRowGather:
+    """The one collective of the PC-sharded sampler: after a step's sweep every rank holds the result rows of its own
+    PCs in its slot of xchg (padded_pcs, n_chains, row_len); all_gather_into_tensor fills in the other ranks' slots.
+    Per step and rank that is ceil(pu / world) * n_chains * (2 d + 6) doubles (cfg5, 8 GPUs: 3 x 1 x 40 x 8 B = 960 B)."""
+
+    def __init__(self, pu, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.begin, self.count, self.cp = pc_shard(pu, self.rank, self.world)
+        self.padded_pcs = self.cp * self.world
+        self.calls = 0
+
+    def __call__(self, xchg):
+        mine = xchg[self.rank * self.cp:(self.rank + 1) * self.cp].clone()
+        self.dist.all_gather_into_tensor(xchg.view(-1), mine.view(-1), group=self.group)
+        self.calls += 1
+
+
+def mcmc_by_pc(engine, n_steps, step, uniforms=None, replay=None, group=None, **kw):
+    """Run engine's chain(s) with the PCs spread over the ranks of `group` (every rank passes the same tables, state
+    and random stream / replay tables, and ends with the same state and draws).  One NCCL all_gather per step."""
+    g = PcRowGather(engine.pu, group)
+    out = engine.run_by_pc(n_steps, step, uniforms=uniforms, replay=replay, shards=[(g.begin, g.count)], gather=g, **kw)
+    out['collective_calls'] = g.calls
+    return out

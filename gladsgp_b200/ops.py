@@ -139,11 +139,8 @@ class McmcEngine:
             th = th.expand(self.n_chains, self.P)
         self.theta.copy_(th)
 
-    def run(self, n_steps, step, uniforms=None, replay=None, do_propMH=True, init_sigwl=True,
-            record=True, record_accept=False, time_kernels=False):
-        """step: (P,) or (n_steps,P) or (n_chains,P) [see step_axes] numpy/tensor of step sizes.
-        uniforms: (n_chains, n_uniform) U[0,1) stream, or replay = dict(cand, logacorr, logu, valid)
-        each (n_steps, n_chains, P).  Returns dict(draws, lp, accepted, consumed)."""
+    def _build_args(self, n_steps, step, uniforms, replay, do_propMH, init_sigwl, record, record_accept):
+        """ggp_mcmc_args for a run of n_steps (SEPIA tables, state, random stream or replay tables, output buffers)."""
         torch, dev = self.torch, 'cuda'
         a = McmcArgs()
         a.m, a.d, a.pu, a.n_chains, a.n_steps = self.m, self.d, self.pu, self.n_chains, int(n_steps)
@@ -204,6 +201,15 @@ class McmcEngine:
             acc = torch.empty((n_steps, self.n_chains, self.P), dtype=torch.uint8, device=dev)
             a.accepted = acc.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        return a, keep, draws, lp, acc
+
+    def run(self, n_steps, step, uniforms=None, replay=None, do_propMH=True, init_sigwl=True,
+            record=True, record_accept=False, time_kernels=False):
+        """step: (P,) or (n_steps,P) or (n_chains,P) [see step_axes] numpy/tensor of step sizes.
+        uniforms: (n_chains, n_uniform) U[0,1) stream, or replay = dict(cand, logacorr, logu, valid)
+        each (n_steps, n_chains, P).  Returns dict(draws, lp, accepted, consumed)."""
+        torch, dev = self.torch, 'cuda'
+        a, keep, draws, lp, acc = self._build_args(n_steps, step, uniforms, replay, do_propMH, init_sigwl, record, record_accept)
         kms = (C.c_double * 2)(0.0, 0.0)
         cnt = None
         if time_kernels:
@@ -216,6 +222,44 @@ class McmcEngine:
                     kernel_ms=(kms[0], kms[1]) if time_kernels else None,
                     eval_count=cnt.cpu().numpy() if cnt is not None else None)
 
+    def run_by_pc(self, n_steps, step, uniforms=None, replay=None, do_propMH=True, init_sigwl=True,
+                  record=True, record_accept=False, shards=None, gather=None):
+        """The same chain(s) with the PCs of every step spread over shards (SURVEY 8e ii; north_star "by independent PC
+        component"): a shard sweeps the betaU / lamUz / lamWs sites and the lamWOs term of its own PCs, the per-PC result
+        rows are exchanged, and every shard closes the step identically (lamWOs decision, record, next candidates).
+
+        shards: list of (pc_begin, pc_count) this process sweeps one after the other (default: all PCs as one shard; a
+        list of several emulates several ranks on one GPU).  gather(xchg): called after this process's shards have written
+        their rows of xchg (pu_padded, n_chains, 2d+6) and before the close -- under torch.distributed it all_gathers the
+        other ranks' rows in place (gladsgp_b200.dist.mcmc_by_pc).  Results are bit-identical to run()."""
+        torch, dev = self.torch, 'cuda'
+        a, keep, draws, lp, acc = self._build_args(n_steps, step, uniforms, replay, do_propMH, init_sigwl, record, record_accept)
+        if shards is None:
+            shards = [(0, self.pu)]
+        rows = self.pu if gather is None else gather.padded_pcs
+        xchg = torch.zeros((rows, self.n_chains, 2 * self.d + 6), dtype=torch.float64, device=dev)
+        a.xchg = xchg.data_ptr()
+        total_steps = int(n_steps)
+        a.n_steps = 1
+        sp = stream_ptr
+        a.pc_begin, a.pc_count = 0, 0
+        check(self.lib.ggp_mcmc_plan_f64(C.byref(a), 0, sp()), 'ggp_mcmc_plan_f64')
+        for t in range(total_steps):
+            a.step_index = t
+            first = True
+            for (b, cnt) in shards:
+                if cnt <= 0:
+                    continue
+                a.pc_begin, a.pc_count = int(b), int(cnt)
+                a.init_sigwl = int(bool(init_sigwl) and t == 0 and first)
+                first = False
+                check(self.lib.ggp_mcmc_run_f64(C.byref(a), sp()), 'ggp_mcmc_run_f64 (PC shard)')
+            if gather is not None:
+                gather(xchg)
+            a.pc_begin, a.pc_count = 0, 0
+            check(self.lib.ggp_mcmc_close_f64(C.byref(a), t, int(t + 1 < total_steps), sp()), 'ggp_mcmc_close_f64')
+        self._keep = keep + [xchg]
+        return dict(draws=draws, lp=lp, accepted=acc, consumed=self.upos, kernel_ms=None, eval_count=None)
 
     def _pinned(self, name, numel, dtype):
         """Cached page-locked host buffer (grown on demand) -> view of `numel` elements."""

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GGP_VERSION 100
+#define GGP_VERSION 200
 
 int ggp_version(void);
 const char* ggp_last_error_string(void);
@@ -115,14 +115,28 @@ typedef struct ggp_mcmc_args {
     size_t workspace_bytes;
     unsigned long long* eval_count; /* device, nullable: [2] += block evaluations done by the sweep launches
                               and by the init / lamWOs-wave launches */
-    double* kernel_ms;     /* HOST pointer, nullable: [2] receives total device time (ms, CUDA events on
-                              `stream`) of the sweep launches and of the lamWOs-wave launches; makes the
-                              call synchronous */
+    double* kernel_ms;     /* HOST pointer, nullable: [0] receives the total device time (ms, CUDA events on
+                              `stream`) of the step kernels, [1] = 0 (the lamWOs terms are part of the step
+                              kernel since version 2); makes the call synchronous */
+    /* PC shard (SURVEY 8e ii: one chain's PCs spread over several GPUs).  pc_count == 0: all PCs, every step is
+     * closed inside the step kernel.  pc_count > 0: this call sweeps only PCs [pc_begin, pc_begin + pc_count) of
+     * ONE step (n_steps must be 1; step_index = its index into step / replay / draws / accepted) and leaves, per
+     * (PC j, chain c), the row  xchg[(j * n_chains + c) * (2 d + 6)] = { betaU[:, j] (d), lamUz[j], lamWs[j],
+     * SigWl[j], SigWl[j] under the candidate lamWOs, accept flags of the d + 2 sites }.  The caller gathers the rows
+     * of all shards (e.g. NCCL all_gather) and closes the step on every rank with ggp_mcmc_close_f64, which unpacks
+     * all pu rows, decides lamWOs, records, and draws the candidates of the next step; ggp_mcmc_plan_f64 draws those
+     * of the first step.  Every rank holds the full state and reaches bit-identical decisions. */
+    int pc_begin, pc_count, step_index, reserved0;
+    double* xchg;          /* device, [pu][n_chains][2 d + 6]; used iff pc_count > 0 */
 } ggp_mcmc_args;
 
 int ggp_sizeof_mcmc_args(void);   /* sizeof(ggp_mcmc_args), for binding self-checks */
 long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains);
 int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream);
+/* PC-sharded stepping (see ggp_mcmc_args.pc_count): candidates of step t; close of step t from the gathered rows
+ * (plan_next != 0: also the candidates of step t + 1). */
+int ggp_mcmc_plan_f64(const ggp_mcmc_args* args, int t, void* stream);
+int ggp_mcmc_close_f64(const ggp_mcmc_args* args, int t, int plan_next, void* stream);
 
 /* ---- (3) posterior prediction ------------------------------------------------------------------
  * SepiaPredict.wPred (A.7, A.10 w_pred; callers assess_all_models.py:489-490,

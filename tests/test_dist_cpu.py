@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from helpers import ROOT  # noqa: F401
-from gladsgp_b200.dist import shard_bounds, all_gather_concat
+from gladsgp_b200.dist import shard_bounds, all_gather_concat, pc_shard, PcRowGather
 
 
 def test_shard_bounds_cover_everything():
@@ -101,3 +101,54 @@ def test_two_rank_sharded_rsvd_matches_single_process():
         np.testing.assert_allclose((U * S) @ Vh, (U0 * S0) @ Vh0, atol=2e-3 * float(S0[0]) / np.sqrt(m))
     np.testing.assert_array_equal(res[0][1], res[1][1])         # U is replicated
     np.testing.assert_array_equal(res[0][3], res[1][3])         # gathered Vh identical on both ranks
+
+
+def test_pc_shard_partition():
+    """PCs of one chain over the ranks: contiguous blocks of ceil(pu / world), every PC owned exactly once."""
+    for pu in (1, 5, 10, 20):
+        for world in (1, 2, 3, 8):
+            owned = []
+            for r in range(world):
+                lo, cnt, cp = pc_shard(pu, r, world)
+                assert cp == -(-pu // world) and 0 <= cnt <= cp and lo == min(pu, r * cp)
+                owned += list(range(lo, lo + cnt))
+            assert owned == list(range(pu))
+
+
+def _pc_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    pu, n_chains, d = 5, 2, 3
+    g = PcRowGather(pu)
+    row = 2 * d + 6
+    xchg = torch.zeros((g.padded_pcs, n_chains, row), dtype=torch.float64)
+    for step in range(3):                                  # one exchange per mcmc_step
+        xchg.zero_()
+        for j in range(g.begin, g.begin + g.count):        # what the rank's sweep leaves for its PCs
+            xchg[j] = 1000.0 * step + 10.0 * j + torch.arange(row, dtype=torch.float64)[None, :] / 100 + \
+                torch.arange(n_chains, dtype=torch.float64)[:, None]
+        g(xchg)
+        q.put((rank, step, xchg[:pu].numpy().copy()))
+    assert g.calls == 3
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pc_row_exchange():
+    """world_size 2 over gloo: every rank ends each step with the rows of all PCs (the sampler's one collective)."""
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(6)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pu, n_chains, row = 5, 2, 12
+    for rank, step, got in res:
+        exp = 1000.0 * step + 10.0 * np.arange(pu)[:, None, None] + np.arange(row)[None, None, :] / 100 + \
+            np.arange(n_chains)[None, :, None]
+        np.testing.assert_array_equal(got, exp)

@@ -24,8 +24,11 @@ def test_do_mcmc_follows_numpy_stream_like_oracle(cuda):
     pr = make_problem(m=64, q=3, pu=2)
     data, model = _build(pr, 3)
     om = so.OracleModel(so.OracleNum(pr['t'], data.sim_data.y_std, pr['K']))
-    # identical lamWOs prior (the oracle's residual sum differs at float32 round-off)
+    # identical lamWOs prior and PC weights (the oracle's pinv / residual sum differ at float32 round-off)
     om.lamWOs.params = [p.copy() for p in model.params.lamWOs.prior.params]
+    om.num.w = np.ascontiguousarray(model._w_pcs.T)
+    om.num.wv = om.num.w.reshape((-1, 1), order='F')
+    om.num.LamSim = np.asarray(model.num.LamSim, dtype=np.float64).copy()      # (float64 vs float32 product of K K^T)
     np.random.seed(7)
     om.do_mcmc(15, rng=np.random)
     after_oracle = np.random.random_sample()
@@ -35,10 +38,14 @@ def test_do_mcmc_follows_numpy_stream_like_oracle(cuda):
     assert after_gpu == after_oracle
     ref = om.get_samples()
     got = model.get_samples()
+    # same accept decisions at every site (a draw changes exactly where the oracle's does); values to the last few ulp:
+    # the candidates come from the same uniforms through exp / log, where CUDA's libm and glibc may differ in the last
+    # bit (under replayed candidates the chains are bit-identical: tests/test_gpu_chains.py)
     for k in ('betaU', 'lamUz', 'lamWs', 'lamWOs'):
         assert got[k].shape == ref[k].shape
-        np.testing.assert_allclose(got[k], ref[k], rtol=1e-7)
-    np.testing.assert_allclose(got['logPost'], ref['logPost'], rtol=1e-7)
+        assert np.array_equal(np.diff(got[k], axis=0) != 0, np.diff(ref[k], axis=0) != 0)
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-12)
+    np.testing.assert_allclose(got['logPost'], ref['logPost'], rtol=1e-10)
     assert model.get_samples(5, nburn=3)['betaU'].shape == (5, 8)
     np.testing.assert_allclose(model.logPost(), ref['logPost'][-1, 0], rtol=1e-7)
 

@@ -27,12 +27,13 @@ def _blocks(num, samples):
     return beta, lamz, dadd, s11, W
 
 
-@pytest.mark.parametrize('m,q,pu,npred', [(64, 3, 2, 5), (100, 8, 5, 4), (257, 4, 2, 37)])
-def test_predict_moments_match_oracle(cuda, m, q, pu, npred):
+@pytest.mark.parametrize('m,q,pu,npred,ns', [(64, 3, 2, 5, 6), (100, 8, 5, 4, 6), (257, 4, 2, 37, 6),
+                                             (512, 8, 10, 256, 2)])      # last: cfg3 model at the reference's largest call size
+def test_predict_moments_match_oracle(cuda, m, q, pu, npred, ns):
     from gladsgp_b200 import ops
     pr = make_problem(m=m, q=q, pu=pu)
     num = pr['num']
-    samples = synthetic.posterior_samples(6, num.d, pu, seed=m)
+    samples = synthetic.posterior_samples(ns, num.d, pu, seed=m)
     tp = synthetic.test_design(npred, q)
     _, mu, Sig = so.w_pred(num, tp, samples, draw=False)
     beta, lamz, dadd, s11, W = _blocks(num, samples)
@@ -42,7 +43,7 @@ def test_predict_moments_match_oracle(cuda, m, q, pu, npred):
     Sg = P.pred_cov(xp, V).cpu().numpy()
     mean = mean.cpu().numpy(); var = var.cpu().numpy()
     scale = np.abs(mu).max()
-    for s in range(6):
+    for s in range(ns):
         for j in range(pu):
             b = s * pu + j
             sl = slice(j * npred, (j + 1) * npred)

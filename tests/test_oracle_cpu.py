@@ -98,3 +98,22 @@ def test_rng_consumption_rule():
     P = tables_from_oracle(mod)['theta'].size
     replay, acc = replay_from_trace(mod.trace, 4, P)
     assert replay['cand'].shape == (4, 1, P) and acc.sum() > 0
+
+
+def test_accept_margins_far_from_ties_at_config_sizes():
+    """The device forms the accept test from per-PC differences, (ll_new - ll_old) + (prior_new - prior_old), where
+    SepiaModel.mcmc_step subtracts two full sums.  The two differ by rounding (~1e-12 absolute); a decision
+    could only flip inside that band.  Over the 13 576 evaluated decisions of the golden chains (cfg1, cfg2, cfg3 sizes)
+    the smallest |margin| = |(clp - lp + log aCorr) - log u| is five orders of magnitude above 1e-9."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    n = 0
+    for cfg in ('cfg1', 'cfg2', 'cfg3'):
+        g = np.load(os.path.join(gold, 'chain_%s.npz' % cfg))
+        mg = g['margin']
+        ok = np.isfinite(mg)
+        assert np.array_equal(ok[:, None, :], g['rp_valid'].astype(bool))
+        assert np.array_equal((mg > 0) & ok, g['chain_acc'][:, 0, :].astype(bool))
+        assert np.min(np.abs(mg[ok])) > 1e-6
+        n += int(ok.sum())
+    assert n >= 10000
