@@ -182,7 +182,7 @@ static __device__ __forceinline__ void panel_gemm(double (&acc)[2][4][2], const 
     //   B: sub-slab lane>>3 (two passes: +0 / +... ) see below
     const int pa_unit = ((lane >> 4) < NU) ? (lane >> 4) : 0;
     const int pa_ks = (lane >> 2) & 3;
-    const int pa_off = rb[pa_unit] * 8 + (lane & 3) * 16;
+    const int pa_off = ((pa_unit == 0) ? rb[0] : rb[1]) * 8 + (lane & 3) * 16;
     const int pb_ks = lane >> 3;                                      // 8 lanes per sub-slab, 2 lines each
     const int pb_off = (row0 + 4 * (lane & 7)) * 8;
     int aoff[NU];
@@ -259,6 +259,15 @@ constexpr int DA_SMALL = (GGP_DA > 4) ? 4 : GGP_DA;      // schedules whose scra
 #ifndef GGP_PD
 #define GGP_PD 2
 #endif
+#ifndef GGP_LATRI
+#define GGP_LATRI 0       // look-ahead product of a diagonal block without its strictly upper 8 x 8 tiles (panel_gemm_cp, TRI):
+                          // 1 = one shared pattern (12 of 16 tiles), 2 = exact patterns (10 of 16), 0 = all 16.  Measured (bit-identical
+                          // results): the extra instantiations cost more (registers, code) than the 6 % of DMMAs they save:
+                          // batched 429 -> 371 / 365 k evaluations/s, sampler 394 -> 389 / 339 k (profiles/README.md)
+#endif
+#ifndef GGP_TAILSPLIT
+#define GGP_TAILSPLIT 0   // pairs at the end of a stage's pool that are handed out as single 8-row units (0: none; measured: no gain)
+#endif
 #ifndef GGP_BL1
 #define GGP_BL1 0         // 1: also pull the B lines of sub-slab s+2 k-blocks into L1 (pays only with a large L1 carve-out)
 #endif
@@ -271,19 +280,31 @@ constexpr int DA_SMALL = (GGP_DA > 4) ? 4 : GGP_DA;      // schedules whose scra
 // cross-lane synchronisation, cp.async.wait_group alone orders the copy before the LDS.128 (conflict-free: consecutive
 // lanes, consecutive 16-byte pieces).  `ring`: per-warp shared memory, DA * NU * 64 doubles (the warp's covariance
 // scratch: idle during the product).  Packed-factor A operand only.
-template <int NU, int DA, int RB = GGP_RB>
+// TRI (diagonal-block product of the look-ahead, NU = 2): strictly upper 8 x 8 tiles of the 32 x 32 block are left out.
+// TRI = 1: the warp's first unit needs column blocks 0..1 only, its second all four -- role 0 takes block rows 0 and 3,
+// role 1 block rows 1 and 2, so ONE pattern (6 of 8 tiles per warp, 12 of the block's 16, of which 10 are needed) serves both
+// warps; TRI = 2 / 3: the exact patterns (rows 0|3: 1 + 4 tiles, rows 1|2: 2 + 3 tiles), two more instantiations that cost
+// more registers than they save DMMAs.  The upper tiles were 6 % of all DMMAs of an evaluation and sat on the critical
+// chain; the tiles that are formed see the same DMMA sequence as before.
+template <int NU, int DA, int RB = GGP_RB, int TRI = 0>
 static __device__ __forceinline__ void panel_gemm_cp(double (&acc)[2][4][2], const double* __restrict__ Ap,
                                                      const double* __restrict__ Lb, const int* __restrict__ soff, int j,
                                                      int row0, const int (&rb)[2], int g, int q, double* __restrict__ ring)
 {
     constexpr int PD = GGP_PD;               // L2 prefetch distance in k-blocks (4 sub-slabs each)
     static_assert(DA == 2 || DA == 4 || DA == 8, "ring depth 2, 4 or 8 sub-slabs");
+    static_assert(TRI == 0 || NU == 2, "triangular form is for a pair");
+    constexpr int NCB = (TRI == 3) ? 3 : 4;                              // column blocks whose B fragments are needed
+    // column blocks of unit i: [0, cbn(i))
+    auto cbn = [](int i) constexpr {
+        return TRI == 0 ? 4 : (TRI == 1 ? (i == 0 ? 2 : 4) : (TRI == 2 ? (i == 0 ? 1 : 4) : (i == 0 ? 2 : 3)));
+    };
     static_assert(4 % RB == 0, "B ring depth must divide the 4 sub-slabs of a k-block");
     const int lane = 4 * g + q;
     const int nsub = 4 * j;
     const int pa_unit = ((lane >> 4) < NU) ? (lane >> 4) : 0;
     const int pa_ks = (lane >> 2) & 3;
-    const int pa_off = rb[pa_unit] * 8 + (lane & 3) * 16;
+    const int pa_off = ((pa_unit == 0) ? rb[0] : rb[1]) * 8 + (lane & 3) * 16;
 #if GGP_BL1
     const int pb_ks = lane >> 3;
     const int pb_off = (row0 + 4 * (lane & 7)) * 8;
@@ -309,7 +330,7 @@ static __device__ __forceinline__ void panel_gemm_cp(double (&acc)[2][4][2], con
         if (t < nsub) {
             const double* sl = Lb + soff[t] + boff;
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) br[t][cb] = *reinterpret_cast<const double2*>(sl + 64 * cb);
+            for (int cb = 0; cb < NCB; ++cb) br[t][cb] = *reinterpret_cast<const double2*>(sl + 64 * cb);
         }
     for (int kb = 0; kb < j; ++kb) {
         if (kb + PD < j) {
@@ -334,7 +355,7 @@ static __device__ __forceinline__ void panel_gemm_cp(double (&acc)[2][4][2], con
             if (s + RB - 1 < nsub) {
                 const double* sbn = Lb + soff[s + RB - 1] + boff;
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) br[(ks + RB - 1) % RB][cb] = *reinterpret_cast<const double2*>(sbn + 64 * cb);
+                for (int cb = 0; cb < NCB; ++cb) br[(ks + RB - 1) % RB][cb] = *reinterpret_cast<const double2*>(sbn + 64 * cb);
             }
             cp_async_wait<DA - 1>();                          // sub-slab s has landed (the DA-1 younger groups may be in flight)
             const int cur = (DA == 8) ? ks + 4 * (kb & 1) : ks % DA;
@@ -345,11 +366,13 @@ static __device__ __forceinline__ void panel_gemm_cp(double (&acc)[2][4][2], con
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-                for (int i = 0; i < NU; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b[cb].x);
+                for (int i = 0; i < NU; ++i)
+                    if (cb < cbn(i)) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, b[cb].x);
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-                for (int i = 0; i < NU; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b[cb].y);
+                for (int i = 0; i < NU; ++i)
+                    if (cb < cbn(i)) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, b[cb].y);
         }
     }
 }
@@ -979,30 +1002,47 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
         __syncthreads();                                                         // (T)
         LA_TICK(1);
         const int nreg = (j >= 0) ? ((Mp - 32 * j) >> 3) - 8 : 0;               // pool units of panel j (multiple of 4)
+        // pool tasks: 16-row pairs, except that the last GGP_TAILSPLIT pairs of the stage are handed out as 8-row units: the
+        // warps reach the end-of-stage barrier within one unit's time of each other instead of one pair's (the barrier
+        // was 20 % of all stall samples, profiles/r2a_sweep_kernel_lines.txt)
+        const int npair = nreg >> 1;
+        const int nsplit = (npair < GGP_TAILSPLIT) ? npair : GGP_TAILSPLIT;
+        const int nwhole = npair - nsplit;                   // tasks 0 .. nwhole-1 are pairs, the next 2 nsplit are units
         int phase = (warp < 2) ? (j >= 0 ? 0 : 1) : 2;       // 0 priority pair, 1 look-ahead pair, 2 pool, 3 inverse (warp 1)
         int pend = 0;        // warp 1: 1 = inverse of block jc still to do, 2 = do it after the pool pair in hand
 
 #pragma unroll 1
         while (true) {
             int cp = j, r0 = 0;
+#if GGP_TAILSPLIT > 0
+            bool single = false;                             // pool task of one 8-row unit (tail of the stage)
+#else
+            constexpr bool single = false;
+#endif
             if (phase == 2) {
                 if (pend == 2) phase = 3;
                 else {
                     int idx = 0;
                     if (lane == 0) idx = atomicAdd(&sm.flag[1], 1);
                     idx = __shfl_sync(0xffffffffu, idx, 0);
-                    if (2 * idx >= nreg) {
+                    if (idx >= nwhole + 2 * nsplit) {
                         if (pend == 0) break;
                         phase = 3;
                     } else {
                         if (pend == 1) pend = 2;
-                        r0 = 32 * j + 64 + 16 * idx;
+#if GGP_TAILSPLIT > 0
+                        single = idx >= nwhole;
+#endif
+                        r0 = 32 * j + 64 + (single ? 16 * nwhole + 8 * (idx - nwhole) : 16 * idx);
                     }
                 }
             } else {
                 cp = (phase == 0) ? j : jc;
                 r0 = 32 * jc + 16 * warp;
             }
+            // look-ahead pair (phase 1): role 0 takes the block's 8-row units 0 and 3, role 1 units 1 and 2 (5 lower tiles each)
+            const bool tri = GGP_LATRI && phase == 1;
+            const int u0 = tri ? warp : 2 * warp, u1 = tri ? 3 - warp : 2 * warp + 1;     // (phase 1 only)
             if (phase == 3) {
                 // warp 1 (after at most one pool pair, which overlaps warp 0's factorisation): inverse of block jc.
                 // Lane k solves Ljj y = e_k, rows in blocks of 8; result D[i][k] and the packed factor's inverse-block
@@ -1048,7 +1088,7 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
                 continue;
             }
             const int row0 = cp << 5;
-            const int rb[2] = {r0, r0 + 8};
+            const int rb[2] = {tri ? 32 * jc + 8 * u0 : r0, tri ? 32 * jc + 8 * u1 : r0 + 8};
             double acc[2][4][2];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -1071,9 +1111,22 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
             // ------------------------------------------------------------------ 1. DMMA update
             LA_TICK(2);
 #if GGP_DA > 0
-            if (cp > 0) panel_gemm_cp<2, GGP_DA>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, scr);
+            if (cp > 0) {
+                if constexpr (GGP_TAILSPLIT > 0) { if (single) panel_gemm_cp<1, GGP_DA>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, scr); }
+                if (single) { }
+#if GGP_LATRI == 2
+                else if (tri && warp == 0) panel_gemm_cp<2, GGP_DA, GGP_RB, 2>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, scr);
+                else if (tri) panel_gemm_cp<2, GGP_DA, GGP_RB, 3>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, scr);
+#elif GGP_LATRI == 1
+                else if (tri) panel_gemm_cp<2, GGP_DA, GGP_RB, 1>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, scr);
+#endif
+                else panel_gemm_cp<2, GGP_DA>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, scr);
+            }
 #else
-            if (cp > 0) panel_gemm<2>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, 0);
+            if (cp > 0) {
+                if constexpr (GGP_TAILSPLIT > 0) { if (single) panel_gemm<1>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, 0); }
+                if (!single) panel_gemm<2>(acc, Lp, Lp, sm.soff, cp, row0, rb, g, q, 0);
+            }
 #endif
 #ifdef GGP_PHASES
             if (acc[0][0][0] + acc[1][3][1] == 1.2345e300) tla__ = 0;
@@ -1082,7 +1135,7 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
             // ------------------------------------------------------------------ 2. covariance, P = C - S (registers)
             {
                 const int rr[2] = {rb[0] + g, rb[1] + g};
-                const bool ok[2] = {rr[0] < m, rr[1] < m};
+                const bool ok[2] = {rr[0] < m, rr[1] < m && !single};   // (a unit task runs the pair code with its second unit masked)
 #if GGP_XPRE
                 pair_cov<2>(acc, X, rr, ok, sm.SC + (cp & 1) * sm.scsz, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane,
                             use_xpre ? xpre : nullptr);
@@ -1102,7 +1155,7 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
                     for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
                         for (int e = 0; e < 2; ++e)
-                            D[(16 * warp + 8 * i + g) * D_LD + 8 * cb + 2 * q + e] = acc[i][cb][e];
+                            D[(8 * (i == 0 ? u0 : u1) + g) * D_LD + 8 * cb + 2 * q + e] = acc[i][cb][e];
                 if (warp == 1) {
                     bar01_arrive(1);                                             // (B) this half of the block is in D
                     pend = 1;                                                    // inverse after at most one pool pair
@@ -1192,6 +1245,7 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
                 const double* __restrict__ ujj = sm.uj + (j & 1) * 32;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
+                    if (i == 1 && single) break;
                     double xt[4][2];
                     unit_trsm(acc[i], xt, sm.Minv, g, q);
                     const int r = rb[i] + g;

@@ -140,38 +140,95 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
     }
 }
 
-// Sigma[b][t1][t2] = S11 - V V^T ; S11 diagonal = s11[b], off-diagonal = cov(xp_t1, xp_t2).
-__global__ void __launch_bounds__(256)
+// Sigma[b][t1][t2] = S11 - V V^T ; S11 diagonal = s11[b], off-diagonal = cov(xp_t1, xp_t2)   (the per-PC block of SEPIA's
+// predictive covariance, SepiaPredict.wPred).  The V V^T contraction (2 n^2 Mp flop per block: at the reference's
+// largest call size, n = 256 designs, as much work as the moments themselves) runs on the FP64 tensor cores: one CTA
+// (4 warps) per 64 x 32 tile of the lower triangle, a warp owns two 8-row units x 32 columns (DMMA.8x8x4, accumulators in
+// registers, fragments are 16-byte loads from the row-major V with the same k permutation as the factorisation); tiles
+// above the diagonal are not computed, every entry is written together with its mirror image.
+__global__ void __launch_bounds__(128)
 pred_cov_kernel(const double* __restrict__ Xp, int n, int d, const double* __restrict__ beta,
                 const double* __restrict__ lamz, const double* __restrict__ s11,
-                const double* __restrict__ V, int Mp, double* __restrict__ Sigma)
+                const double* __restrict__ V, int Mp, double* __restrict__ Sigma, int n_ct, int n_tiles)
 {
-    const int b = blockIdx.z;
-    const int t1 = blockIdx.y * 16 + (threadIdx.x >> 4);
-    const int t2 = blockIdx.x * 16 + (threadIdx.x & 15);
-    if (t1 >= n || t2 >= n) return;
-    const double* v1 = V + ((size_t)b * n + t1) * Mp;
-    const double* v2 = V + ((size_t)b * n + t2) * Mp;
-    double s0 = 0.0, s1 = 0.0;
-    for (int k = 0; k < Mp; k += 2) {
-        const double2 a = *reinterpret_cast<const double2*>(v1 + k);
-        const double2 c = *reinterpret_cast<const double2*>(v2 + k);
-        s0 = fma(a.x, c.x, s0);
-        s1 = fma(a.y, c.y, s1);
+    const int b = blockIdx.x / n_tiles;
+    const int tile = blockIdx.x - b * n_tiles;
+    // tiles of the lower triangle in row-tile-major order: row tile rt has min(n_ct, 2 rt + 2) column tiles
+    int rt = 0, ct = tile;
+    while (true) {
+        const int w = min(n_ct, 2 * rt + 2);
+        if (ct < w) break;
+        ct -= w; ++rt;
     }
-    double c11;
-    if (t1 == t2) {
-        c11 = s11[b];
-    } else {
-        const double* be = beta + (size_t)b * d;
-        double dist = 0.0;
-        for (int k = 0; k < d; ++k) {
-            double df = Xp[(size_t)t1 * d + k] - Xp[(size_t)t2 * d + k];
-            dist = fma(be[k] * df, df, dist);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int row0 = 64 * rt + 16 * warp, col0 = 32 * ct;
+    if (col0 > row0 + 15) return;                      // this warp's rows lie entirely above the tile's columns
+    const double* Vb = V + (size_t)b * n * Mp;
+    const double* ap[2];
+    const double* bp[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) ap[i] = Vb + (size_t)min(row0 + 8 * i + g, n - 1) * Mp + 2 * q;
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) bp[cb] = Vb + (size_t)min(col0 + 8 * cb + g, n - 1) * Mp + 2 * q;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) { acc[i][cb][0] = 0.0; acc[i][cb][1] = 0.0; }
+    double2 a[2], bb[4], an[2], bn[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const double2*>(ap[i]);
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) bb[cb] = *reinterpret_cast<const double2*>(bp[cb]);
+    for (int k = 0; k < Mp; k += 8) {
+        if (k + 8 < Mp) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) an[i] = *reinterpret_cast<const double2*>(ap[i] + k + 8);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) bn[cb] = *reinterpret_cast<const double2*>(bp[cb] + k + 8);
         }
-        c11 = exp(-dist) / lamz[b];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].x, bb[cb].x);
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) dmma884(acc[i][cb][0], acc[i][cb][1], a[i].y, bb[cb].y);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = an[i];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) bb[cb] = bn[cb];
     }
-    Sigma[((size_t)b * n + t1) * n + t2] = c11 - (s0 + s1);
+    const double* be = beta + (size_t)b * d;
+    const double il = 1.0 / lamz[b];
+    double* Sb = Sigma + (size_t)b * n * n;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int t1 = row0 + 8 * i + g;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int t2 = col0 + 8 * cb + 2 * q + e;
+                if (t1 >= n || t2 > t1) continue;
+                double c11;
+                if (t1 == t2) {
+                    c11 = s11[b];
+                } else {
+                    double dist = 0.0;
+                    for (int kk = 0; kk < d; ++kk) {
+                        const double df = Xp[(size_t)t1 * d + kk] - Xp[(size_t)t2 * d + kk];
+                        dist = fma(be[kk] * df, df, dist);
+                    }
+                    c11 = exp(-dist) * il;
+                }
+                const double v = c11 - acc[i][cb][e];
+                Sb[(size_t)t1 * n + t2] = v;
+                if (t1 != t2) Sb[(size_t)t2 * n + t1] = v;
+            }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,7 +503,7 @@ int ggp_predict_f64(const double* X, int m, int d, const double* factor, const d
     const int Mp = round_up32(m);
     const size_t smem = pred_smem_bytes(d);
     if (smem > 100 * 1024) {
-        set_error("ggp_predict_f64: m=%d d=%d needs %zu B of shared memory (> 227 KB)", m, d, smem);
+        set_error("ggp_predict_f64: m=%d d=%d needs %zu B of shared memory (> 100 KB)", m, d, smem);
         return GGP_ERR_UNSUPPORTED;
     }
     const long long need = ggp_predict_workspace_bytes(m, n, B);
@@ -467,8 +524,12 @@ int ggp_pred_cov_f64(const double* Xp, int n, int d, const double* beta, const d
 {
     GGP_ARG(Xp && beta && lamz && s11_diag && V && Sigma_out, "null pointer");
     GGP_ARG(n > 0 && d > 0 && m > 0 && B > 0, "n, d, m, B must be positive");
-    dim3 grid((n + 15) / 16, (n + 15) / 16, B);
-    pred_cov_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Xp, n, d, beta, lamz, s11_diag, V, round_up32(m), Sigma_out);
+    const int n_rt = (n + 63) / 64, n_ct = (n + 31) / 32;
+    long long n_tiles = 0;
+    for (int rt = 0; rt < n_rt; ++rt) n_tiles += (n_ct < 2 * rt + 2) ? n_ct : 2 * rt + 2;
+    GGP_ARG(n_tiles * (long long)B < (1LL << 31), "B * tiles(n) must be below 2^31 CTAs");
+    pred_cov_kernel<<<(unsigned)(n_tiles * B), 128, 0, (cudaStream_t)stream>>>(Xp, n, d, beta, lamz, s11_diag, V, round_up32(m),
+                                                                              Sigma_out, n_ct, (int)n_tiles);
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }

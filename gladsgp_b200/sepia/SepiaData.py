@@ -232,9 +232,10 @@ class SepiaData:
                     # np.std(y - y_mean, ddof=1) over all elements, from the column sums
                     cmh = cm.double().cpu().numpy()
                     ss = float(np.sum(cs.double().cpu().numpy() ** 2) * (m - 1))
-                    if np.ndim(y_mean) == 0 or not center:
-                        resid_mean = cmh - np.asarray(y_mean, dtype=np.float64)
-                        ss += m * float(np.sum((resid_mean - resid_mean.mean()) ** 2))
+                    # between-column part: column means of the residual y - y_mean about their grand mean (zero when
+                    # y_mean is the column mean; non-zero for a scalar, a user-supplied vector, or center=False)
+                    resid_mean = cmh - np.asarray(y_mean, dtype=np.float64).reshape(-1)
+                    ss += m * float(np.sum((resid_mean - resid_mean.mean()) ** 2))
                     y_sd = np.float32(np.sqrt(ss / (m * n - 1)))
         mean_h = np.asarray(y_mean, dtype=np.float32).reshape(-1)
         sd_h = np.asarray(y_sd, dtype=np.float32).reshape(-1)

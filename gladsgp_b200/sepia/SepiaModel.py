@@ -104,7 +104,14 @@ class SepiaModel:
         num.n_y = n_y
         self._set_params_sim_only(m, n_y, resid_ss)
         self._engine = None
+        self._pred_cache = None          # (key, ops.Predictor, nsamp): factors of the last set of posterior samples predicted with
         self.launches = 0
+
+    def __getstate__(self):              # device-side caches do not travel in pickles / deep copies
+        st = dict(self.__dict__)
+        st['_engine'] = None
+        st['_pred_cache'] = None
+        return st
 
     # ------------------------------------------------------------------ parameters
     def _set_params_sim_only(self, m, n_y, resid_ss):

@@ -8,16 +8,42 @@ fit_scalar_models.py:481-483; include_trunc_error.py:86-88.
 Differences from the reference implementation, all behind the same results:
 * every (sample, PC) covariance is factored ONCE per prediction object (SEPIA re-solves S22 for
   every call) and test designs are pushed through the cached factor on the GPU;
-* the multivariate-normal realisation uses an eigen-factor of each per-PC covariance block instead of
-  one SVD of the block-diagonal matrix: same distribution, and the same np.random.normal draws are
-  consumed, but a realisation is not bit-comparable with SEPIA's (SVD sign ambiguity, SURVEY 7.2);
-  parity is asserted on mu / Sigma (storeMuSigma=True).
+* the factors are kept with the model and re-used by later prediction objects built from the same samples
+  (the reference's callers build one object per batch of test designs, assess_all_models.py:476-492);
+* the multivariate-normal realisation uses a Cholesky factor of each per-PC covariance block (positive
+  definite: Sigma >= I / lamWs) instead of one SVD of the block-diagonal matrix: same distribution, and
+  the same np.random.normal draws are consumed, but a realisation is not bit-comparable with SEPIA's
+  (SVD sign ambiguity); parity is asserted on mu / Sigma (storeMuSigma=True).
 """
+import warnings
+
 import numpy as np
 
 from .. import ops, _lib
 
-MAX_JOINT = 1024      # above this many designs per call the joint covariance is not formed
+MAX_JOINT = 1024      # above this many designs per call the joint covariance is not formed unless joint=True is passed
+
+
+def _samples_key(samples, model, add_resid):
+    """Identity of a (model, posterior samples) pair: the callers of the reference construct one prediction object per
+    batch of test designs with the same samples (assess_all_models.py:476-492), so the nsamp x pu factorisations are kept
+    with the model and re-used while the sample arrays are unchanged (same objects, same shapes, same checksums)."""
+    parts = [id(model), bool(add_resid)]
+    for k in ('betaU', 'lamUz', 'lamWs', 'lamWOs'):
+        a = np.asarray(samples[k])
+        parts += [k, a.shape, a.dtype.str, float(np.sum(a, dtype=np.float64)), float(np.sum(np.square(a, dtype=np.float64)))]
+    return tuple(parts)
+
+
+def _pinned(owner, name, numel):
+    """Cached page-locked float64 staging buffer kept with the predictor (page-locking per call costs more than the copy)."""
+    import torch
+    pool = owner.__dict__.setdefault('_pin', {})
+    buf = pool.get(name)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(max(int(numel), 1), dtype=torch.float64).pin_memory()
+        pool[name] = buf
+    return buf[:numel]
 
 
 class SepiaPrediction:
@@ -98,12 +124,27 @@ class SepiaEmulatorPrediction(SepiaPrediction):
         num = self.model.num
         pu = num.pu
         npred = self.xpredt.shape[0]
-        ns, beta, lamz, dadd, s11, W = self._blocks()
-        self._pred = ops.Predictor(num.zt, W, beta, lamz, dadd, s11)
-        bad = int((self._pred.info != 0).sum().item())
-        if bad:
-            raise np.linalg.LinAlgError('%d of %d (sample, PC) covariance matrices are not positive definite' %
-                                        (bad, ns * pu))
+        key = _samples_key(self.samples, self.model, self.addResidVar)
+        cached = getattr(self.model, '_pred_cache', None)
+        if cached is not None and cached[0] == key:
+            self._pred, ns = cached[1], cached[2]
+        else:
+            ns, beta, lamz, dadd, s11, W = self._blocks()
+            self._pred = ops.Predictor(num.zt, W, beta, lamz, dadd, s11)
+            bad = int((self._pred.info != 0).sum().item())
+            if bad:
+                raise np.linalg.LinAlgError('%d of %d (sample, PC) covariance matrices are not positive definite' %
+                                            (bad, ns * pu))
+            self.model._pred_cache = (key, self._pred, ns)
+        if self.joint is None and npred > MAX_JOINT:
+            # SEPIA draws one joint realisation over all designs of a call; above MAX_JOINT designs the npred x npred blocks
+            # (nsamp*pu of them) are not formed unless asked for: say so instead of changing the distribution silently
+            if self.storeMuSigma:
+                raise ValueError('storeMuSigma with %d > %d designs per call needs the joint covariance: pass joint=True '
+                                 '(memory: nsamp*pu*npred^2 doubles) or joint=False for marginal variances' % (npred, MAX_JOINT))
+            warnings.warn('SepiaEmulatorPrediction: %d designs in one call (> %d): realisations are drawn from the marginal '
+                          'predictive distributions (no cross-design covariance); pass joint=True for SEPIA\'s joint draw or '
+                          'split the designs into smaller calls' % (npred, MAX_JOINT), RuntimeWarning, stacklevel=3)
         joint = self.joint if self.joint is not None else (npred <= MAX_JOINT)
         if joint and npred > 1:
             mean, var, V = self._pred.predict(self.xpredt, want_V=True)
@@ -123,17 +164,31 @@ class SepiaEmulatorPrediction(SepiaPrediction):
                 sl = slice(j * npred, (j + 1) * npred)
                 self.sigma[:, sl, sl] = blk[:, j]
         if self.storeRlz:
-            # one np.random.normal(size=npred*pu) per sample, in sample order, as SEPIA's rmultnormsvd
-            z = np.stack([np.random.normal(size=npred * pu) for _ in range(ns)])
-            zd = torch.as_tensor(z.reshape(ns, pu, npred), device='cuda')
+            # SEPIA's rmultnormsvd consumes one np.random.normal(size=npred*pu) per sample, in sample order: the legacy
+            # stream is the same for one call of ns*npred*pu values (tests/test_host_cpu.py)
+            z = np.random.normal(size=ns * npred * pu)
+            eng = self._pred
+            stage = _pinned(eng, 'z', z.size)
+            stage.copy_(torch.from_numpy(z))
+            zd = stage.to('cuda', non_blocking=True).reshape(ns, pu, npred)
             if Sig is not None:
-                lam, Q = torch.linalg.eigh(Sig.reshape(ns, pu, npred, npred))
-                a = torch.sqrt(torch.clamp(lam, min=0.0)) * zd
-                dev = torch.einsum('spij,spj->spi', Q, a)
+                # realisation = mean + F z with F F^T = Sigma.  Sigma >= I / lamWs is positive definite, so the factor is a
+                # Cholesky factor (SEPIA uses U sqrt(s) of an SVD: the same distribution; neither is bit-comparable across
+                # implementations); the eigen-factor stays as the fall-back for a block cuSOLVER rejects
+                S4 = Sig.reshape(ns, pu, npred, npred)
+                L, info = torch.linalg.cholesky_ex(S4)
+                if bool((info != 0).any().item()):
+                    lam, Qm = torch.linalg.eigh(S4)
+                    dev = torch.einsum('spij,spj->spi', Qm, torch.sqrt(torch.clamp(lam, min=0.0)) * zd)
+                else:
+                    dev = torch.matmul(L, zd.unsqueeze(-1)).squeeze(-1)
             else:
                 dev = torch.sqrt(torch.clamp(var.reshape(ns, pu, npred), min=0.0)) * zd
             w = (mean + dev).permute(0, 2, 1).contiguous()           # (ns, npred, pu)
-            self.w = w.cpu().numpy()
+            out = _pinned(eng, 'w', w.numel())
+            out.copy_(w.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.w = out.numpy().reshape(ns, npred, pu).copy()
 
     # ------------------------------------------------------------------ outputs
     def get_w(self):

@@ -25,6 +25,11 @@ def test_reference_arm_prints_contract_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and d['dtype'] == 'f64'
+    # both host modes are reported (one chain x all BLAS threads; one single-thread chain per core), value = the better one
+    modes = d['cpu_baseline']['modes']
+    assert set(modes) == {'one_chain', 'per_core_chains'}
+    assert modes['one_chain']['chains'] == 1 and modes['per_core_chains']['blas_threads'] == 1
+    assert d['value'] == max(v['value'] for v in modes.values())
 
 
 def test_reference_arm_is_silent_on_other_ranks():

@@ -135,6 +135,11 @@ def test_device_path_of_the_api_equals_host_path(cuda, monkeypatch):
     d3 = SepiaData(t_sim=pr['t'], y_sim=y, y_ind_sim=np.linspace(0, 1, y.shape[1]))
     d3.standardize_y(scale='columnwise')
     np.testing.assert_allclose(d3.sim_data.orig_y_sd, np.std(y.astype(np.float64), ddof=1, axis=0), rtol=1e-6)
+    # user-supplied vector mean that is NOT the column mean, scalar sd left to the library: np.std(y - y_mean, ddof=1)
+    shifted = (np.mean(y, axis=0) + np.linspace(-0.3, 0.4, y.shape[1])).astype(np.float32)
+    d4 = SepiaData(t_sim=pr['t'], y_sim=y, y_ind_sim=np.linspace(0, 1, y.shape[1]))
+    d4.standardize_y(y_mean=shifted)
+    np.testing.assert_allclose(d4.sim_data.orig_y_sd, np.std(y.astype(np.float64) - shifted.astype(np.float64), ddof=1), rtol=1e-6)
 
 
 def test_init_model_on_device(cuda, tmp_path, monkeypatch):

@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 import numpy as np
 import pytest
 
@@ -158,3 +159,57 @@ def test_library_exports_every_declared_symbol():
     assert h.ggp_cov_build_f64(None, 4, 2, None, None, None, 1, None, None) == -1
     assert b'null pointer' in h.ggp_last_error_string()
     assert ctypes.sizeof(_lib.McmcArgs) == h.ggp_sizeof_mcmc_args()
+
+
+def test_legacy_normal_stream_is_call_size_invariant():
+    """SepiaPredict draws the realisations of all samples with ONE np.random.normal call where SEPIA makes one call per
+    sample: the legacy global stream (polar Box-Muller with its cached second value) gives the same numbers either way."""
+    for per_call in (1, 3, 7, 10):
+        np.random.seed(11)
+        a = np.concatenate([np.random.normal(size=per_call) for _ in range(9)])
+        np.random.seed(11)
+        b = np.random.normal(size=9 * per_call)
+        assert np.array_equal(a, b)
+        assert np.random.random_sample() == (np.random.seed(11), np.random.normal(size=9 * per_call), np.random.random_sample())[2]
+
+
+def test_normal_proposals_are_rejected_loudly():
+    """The device sampler implements the proposal kinds of the GladsGP path (Uniform, BetaRho, PropMH); a parameter with
+    a Normal step type must not be mis-sampled silently."""
+    from gladsgp_b200.ops import PROP_KIND
+    assert 'Normal' not in PROP_KIND and set(PROP_KIND) == {'Uniform', 'BetaRho', 'PropMH'}
+    src = open(os.path.join(ROOT, 'gladsgp_b200', 'sepia', 'SepiaModel.py')).read()
+    assert "if b.mcmc.stepType not in PROP_KIND:" in src and 'raise NotImplementedError' in src
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='reference tree not present (GPU box)')
+def test_reference_modules_resolve_against_the_shim():
+    """`import src.model` from the reference tree binds every sepia name it uses to this repository's mirror, and the
+    functions the reference calls exist with the argument names it passes (src/model.py:13-15,57-106,225-238;
+    assess_all_models.py:468-492)."""
+    import importlib
+    import inspect
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(1, '/root/reference');"
+        "import src.model as rm; import sepia, inspect;"
+        "assert rm.SepiaModel.__module__.startswith('gladsgp_b200.sepia');"
+        "assert rm.SepiaData.__module__.startswith('gladsgp_b200.sepia');"
+        "assert callable(rm.SepiaParam);"
+        "print(sorted(n for n in dir(rm) if not n.startswith('_'))[:40])" % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for name in ('init_model', 'fit_models', 'load_model'):
+        assert name in r.stdout
+    from sepia.SepiaModel import SepiaModel
+    from sepia.SepiaData import SepiaData
+    from sepia.SepiaPredict import SepiaEmulatorPrediction
+    from sepia import SepiaParam
+    assert {'t_sim', 'y_sim', 'y_ind_sim'} <= set(inspect.signature(SepiaData.__init__).parameters)
+    assert {'y_mean', 'y_sd'} <= set(inspect.signature(SepiaData.standardize_y).parameters)
+    assert 'K' in inspect.signature(SepiaData.create_K_basis).parameters
+    assert list(inspect.signature(SepiaModel.tune_step_sizes).parameters)[1:3] == ['n_burn', 'n_levels']
+    assert {'numsamples', 'nburn'} <= set(inspect.signature(SepiaModel.get_samples).parameters)
+    assert {'t_pred', 'samples', 'model'} <= set(inspect.signature(SepiaEmulatorPrediction.__init__).parameters)
+    assert {'val', 'name', 'val_shape', 'dist', 'params', 'bounds', 'mcmcStepParam', 'mcmcStepType'} <= \
+        set(inspect.signature(SepiaParam.__init__).parameters)

@@ -57,7 +57,7 @@ def main():
         res['loglik_B%d' % B] = dict(ms=round(best, 4), kevals_s=round(B / best, 1), kevals_s_med=round(B / med, 1),
                                      tflops=round(B * flop_eval / best / 1e9, 2), sha=digest(ll))
         del ws
-    chains = int(os.environ.get('GGP_CHAINS', '236'))
+    chains = int(str(os.environ.get('GGP_CHAINS', '236')).split(',')[0])
     steps = int(os.environ.get('GGP_STEPS', '10'))
     if chains > 0:
         from gladsgp_b200 import svd, model as gmodel
