@@ -300,6 +300,182 @@ sweep_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ Lws, long long l_str
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Speculative step kernel for FEW chains (the reference's own workload is ONE chain, src/model.py:234-235): the sites of a
+// PC are inherently sequential, and with a handful of matrices in flight most of the GPU idles.  Three thread-block
+// clusters ("lanes") per (PC, chain) evaluate, in every round, the next TWO evaluations of the PC's sequence:
+//   lane 0: evaluation e0 under the current state;
+//   lane 1: evaluation e1 under the state in which e0's candidate was accepted;  lane 2: e1 under the unchanged state.
+// After the round every lane reads the three results, takes e0's decision, picks the matching e1 result, takes e1's
+// decision -- the arithmetic of the sequential sweep, evaluation by evaluation, so the chain is bit-identical -- and
+// updates its private copy of the PC's state.  A round costs one evaluation's latency and retires two.  
+// The lanes of a PC meet at a counter in global memory once per round; all clusters of the launch must be resident at the
+// same time (the host checks cudaOccupancyMaxActiveClusters before choosing this kernel, and the wait is bounded).
+// Sequence of a PC: its valid betaU sites, lamUz, lamWs (validity is known from the plan), then its term under the candidate
+// lamWOs (no decision here: that is the close of the step).
+// ---------------------------------------------------------------------------------------------
+constexpr int SPEC_LANES = 3;
+constexpr int SPEC_MAXEV = 72;          // d + 3 <= 67
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// st = private state of one lane: [0, d) betaU[:, j], [d] lamUz[j], [d + 1] lamWs[j], [d + 2] SigWl[j];  evaluation index
+// e: e < d betaU element, d lamUz, d + 1 lamWs, d + 2 lamWOs.  Up to two entries are replaced by candidates.
+__device__ inline void gather_spec(const ggp_mcmc_args& a, const double* st, double lamwos_cur, int c, int j,
+                                   int ea, double ca, int eb, double cb, double* beta_sm, double& lamz, double& diag_add)
+{
+    const int d = a.d;
+    if (threadIdx.x < d) {
+        const int e = threadIdx.x;
+        beta_sm[e] = (e == ea) ? ca : ((e == eb) ? cb : st[e]);
+    }
+    lamz = (ea == d) ? ca : ((eb == d) ? cb : st[d]);
+    const double lamws = (ea == d + 1) ? ca : ((eb == d + 1) ? cb : st[d + 1]);
+    const double lamwos = (ea == d + 2) ? ca : ((eb == d + 2) ? cb : lamwos_cur);
+    diag_add = 1.0 / (chain_lamsim(a, c, j) * lamwos) + 1.0 / lamws;
+}
+
+struct SpecWs {
+    double* res;        // [n_chains][pu][2][4]   results of a round, by round parity and lane
+    unsigned* cnt;      // [n_chains][pu]         arrivals (3 per round; zeroed by the host before every run)
+    double* state;      // [n_chains][pu][3][d + 3]
+    double* Lws;        // [n_chains][pu][3] factor workspaces
+};
+
+template <int RA>
+__global__ void __launch_bounds__(NT, GGP_CL_CTAS_PER_SM)
+sweep_spec_kernel(ggp_mcmc_args a, Plan pl, SpecWs sw, long long l_stride, double* __restrict__ sig_cand,
+                  unsigned* __restrict__ arrive, int t, unsigned round_base)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double beta_sm[64];
+    __shared__ int ev_sm[SPEC_MAXEV];
+    __shared__ int nev_sm;
+    const int Mp = round_up32(a.m);
+    const int G = (int)cluster_nctarank();
+    const int cl = blockIdx.x / G;                       // cluster index along x: (PC, lane)
+    const int j = cl / SPEC_LANES, lane_id = cl - j * SPEC_LANES, c = blockIdx.y;
+    const bool lead = (threadIdx.x == 0) && (cluster_ctarank() == 0);
+    const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
+    const int E = d + 3;                                  // evaluations of the PC's sequence (last = lamWOs term)
+    double* th = a.theta + (size_t)c * P;
+    double* st = sw.state + (((size_t)c * pu + j) * SPEC_LANES + lane_id) * (d + 3);
+    double* Lp = sw.Lws + (((size_t)c * pu + j) * SPEC_LANES + lane_id) * l_stride;
+    double* res = sw.res + ((size_t)c * pu + j) * 8;
+    unsigned* cnt = sw.cnt + (size_t)c * pu + j;
+    const double* wj = chain_w(a, c, j);
+    unsigned char* accd = a.accepted ? a.accepted + ((size_t)t * a.n_chains + c) * P : nullptr;
+    const double lamwos_cur = th[P - 1];
+    auto site_of = [&](int e) { return e < d ? j * d + e : (e == d ? d * pu + j : (e == d + 1 ? d * pu + pu + j : P - 1)); };
+
+    // private state and the list of valid evaluations (identical in the three lanes)
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int e = 0; e < E; ++e) {
+            if (pl.valid[(size_t)c * P + site_of(e)]) ev_sm[n++] = e;
+            else if (lead && accd && lane_id == 0 && e < d + 2) accd[site_of(e)] = 0;
+        }
+        nev_sm = n;
+        if (cluster_ctarank() == 0) {
+            for (int e = 0; e < d; ++e) st[e] = th[j * d + e];
+            st[d] = th[d * pu + j];
+            st[d + 1] = th[d * pu + pu + j];
+            st[d + 2] = a.sigwl[(size_t)c * pu + j];
+        }
+    }
+    cluster_sync_all();
+    const int nev = nev_sm;
+    const int nrounds = (nev + 1) >> 1;
+
+    for (int r = 0; r < nrounds; ++r) {
+        const int e0 = ev_sm[2 * r];
+        const int e1 = (2 * r + 1 < nev) ? ev_sm[2 * r + 1] : -1;
+        const size_t o0 = (size_t)c * P + site_of(e0);
+        const size_t o1 = (e1 >= 0) ? (size_t)c * P + site_of(e1) : 0;
+        const double c0 = pl.cand[o0];
+        const double c1 = (e1 >= 0) ? pl.cand[o1] : 0.0;
+        // this lane's evaluation of the round
+        const bool work = (lane_id == 0) || (e1 >= 0);
+        double ll = 0.0;
+        if (work) {
+            double lamz, diag_add;
+            __syncthreads();
+            if (lane_id == 0) gather_spec(a, st, lamwos_cur, c, j, e0, c0, -1, 0.0, beta_sm, lamz, diag_add);
+            else if (lane_id == 1) gather_spec(a, st, lamwos_cur, c, j, e0, c0, e1, c1, beta_sm, lamz, diag_add);
+            else gather_spec(a, st, lamwos_cur, c, j, e1, c1, -1, 0.0, beta_sm, lamz, diag_add);
+            __syncthreads();
+            ll = eval_dispatch<true, false, RA>(smem_raw, a.X, a.m, Mp, d, beta_sm, lamz, diag_add, wj, Lp, 0);
+        }
+        if (lead) {
+            if (work && a.eval_count) atomicAdd(a.eval_count, 1ULL);
+            double* slot = res + (r & 1) * 4;
+            slot[lane_id] = ll;
+            __threadfence();
+            atomicAdd(cnt, 1u);
+            const unsigned target = (round_base + (unsigned)r + 1u) * SPEC_LANES;
+            const long long t0 = clock64();
+            bool ok = true;
+            while ((int)(ld_acquire_u32(cnt) - target) < 0) {
+                if (clock64() - t0 > (1LL << 33)) { ok = false; break; }          // ~4 s: a lane is not resident (never expected)
+            }
+            const double l0 = __ldcg(slot + 0), l1a = __ldcg(slot + 1), l1r = __ldcg(slot + 2);
+            if (!ok && a.lp_draws) a.lp_draws[(size_t)t * a.n_chains + c] = NAN;
+            // decision of e0, then of e1: the sequential sweep's arithmetic
+            bool acc0 = false;
+            if (e0 == d + 2) {
+                if (lane_id == 0) sig_cand[(size_t)c * pu + j] = l0;
+            } else {
+                const int s0 = site_of(e0);
+                const size_t po = chain_prior_off(a, c) + s0;
+                const double dprior = elem_log_prior(a.prior_kind[s0], a.prior_a[po], a.prior_b[po], c0) -
+                                      elem_log_prior(a.prior_kind[s0], a.prior_a[po], a.prior_b[po], st[e0]);
+                acc0 = pl.logu[o0] < ((l0 - st[d + 2]) + dprior) + pl.lacorr[o0];
+                if (acc0) { st[e0] = c0; st[d + 2] = l0; }
+                if (accd && lane_id == 0) accd[s0] = acc0 ? 1 : 0;
+            }
+            if (e1 >= 0) {
+                const double l1 = acc0 ? l1a : l1r;
+                if (e1 == d + 2) {
+                    if (lane_id == 0) sig_cand[(size_t)c * pu + j] = l1;
+                } else {
+                    const int s1 = site_of(e1);
+                    const size_t po = chain_prior_off(a, c) + s1;
+                    const double dprior = elem_log_prior(a.prior_kind[s1], a.prior_a[po], a.prior_b[po], c1) -
+                                          elem_log_prior(a.prior_kind[s1], a.prior_a[po], a.prior_b[po], st[e1]);
+                    const bool acc1 = pl.logu[o1] < ((l1 - st[d + 2]) + dprior) + pl.lacorr[o1];
+                    if (acc1) { st[e1] = c1; st[d + 2] = l1; }
+                    if (accd && lane_id == 0) accd[s1] = acc1 ? 1 : 0;
+                }
+            }
+        }
+        cluster_sync_all();              // the lane's state is visible to every CTA of its cluster
+    }
+    if (lead) {
+        // every launch adds the same number of arrivals to the counter, whatever the number of valid evaluations
+        const int rcap = (E + 1) >> 1;
+        if (nrounds < rcap) atomicAdd(cnt, (unsigned)(rcap - nrounds));
+        if (lane_id == 0) {
+            for (int e = 0; e < d; ++e) th[j * d + e] = st[e];
+            th[d * pu + j] = st[d];
+            th[d * pu + pu + j] = st[d + 1];
+            a.sigwl[(size_t)c * pu + j] = st[d + 2];
+            __threadfence();
+            const unsigned prev = atomicAdd(&arrive[c], 1u);
+            if (prev == (unsigned)pu - 1u) {
+                arrive[c] = 0u;
+                __threadfence();
+                finalize_chain(a, pl, sig_cand, t, c);
+                if (t + 1 < a.n_steps) plan_chain(a, pl, t + 1, c);
+            }
+        }
+    }
+}
+
 // mode 0: sigwl <- per-PC terms of the current state.  mode 1: sigwl_cand <- terms under candidate lamWOs.
 template <bool CL, bool LA = false, int RA = GGP_RA>
 __global__ void __launch_bounds__(NT, CL ? GGP_CL_CTAS_PER_SM : GGP_CTAS_PER_SM)
@@ -361,10 +537,26 @@ __global__ void close_kernel(ggp_mcmc_args a, Plan pl, double* __restrict__ sig_
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Cluster size of the speculative step kernel (0: not used).  It needs 3 clusters per (PC, chain), all resident at once;
+// a round retires two evaluations, so it pays when its clusters are more than half as large as those of the plain cluster
+// kernel would be (cfg3, one chain: 30 clusters of 8 CTAs against 10 of 8; cfg5, one chain: 60 of 4 against 20 of 16 -- no).
+// GGP_SPEC=0 in the environment switches it off.
+static int spec_cluster_size(int pu, int n_chains, int Mp, int d)
+{
+    if (const char* e = getenv("GGP_SPEC")) { if (atoi(e) == 0) return 0; }
+    if (d + 3 > SPEC_MAXEV) return 0;
+    const int g_plain = choose_cluster((long long)pu * n_chains, Mp);
+    if (g_plain <= 1) return 0;
+    const int g_spec = choose_cluster((long long)SPEC_LANES * pu * n_chains, Mp);
+    return (g_spec >= 2 && 2 * g_spec > g_plain) ? g_spec : 0;
+}
+
 // workspace carve-up shared by the entry points
 struct McmcWs {
-    double* Lws; Plan pl; double* sig_cand; unsigned* arrive;
+    double* Lws; Plan pl; double* sig_cand; unsigned* arrive; SpecWs spec;
 };
+long long workspace_bytes_impl(int m, int d, int pu, int n_chains, bool with_spec);
+
 static McmcWs carve_ws(const ggp_mcmc_args& a)
 {
     const int Mp = round_up32(a.m);
@@ -378,7 +570,16 @@ static McmcWs carve_ws(const ggp_mcmc_args& a)
     w.pl.logu = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * P * sizeof(double));
     w.pl.valid = reinterpret_cast<int*>(p);     p += align256((size_t)a.n_chains * P * sizeof(int));
     w.sig_cand = reinterpret_cast<double*>(p);  p += align256((size_t)a.n_chains * a.pu * sizeof(double));
-    w.arrive = reinterpret_cast<unsigned*>(p);
+    w.arrive = reinterpret_cast<unsigned*>(p);  p += align256((size_t)a.n_chains * sizeof(unsigned));
+    w.spec.res = nullptr; w.spec.cnt = nullptr; w.spec.state = nullptr; w.spec.Lws = nullptr;
+    // (a workspace sized while the speculative kernel was switched off simply runs without it)
+    if (spec_cluster_size(a.pu, a.n_chains, Mp, a.d) > 0 &&
+        (long long)a.workspace_bytes >= workspace_bytes_impl(a.m, a.d, a.pu, a.n_chains, true)) {
+        w.spec.res = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * a.pu * 8 * sizeof(double));
+        w.spec.cnt = reinterpret_cast<unsigned*>(p); p += align256((size_t)a.n_chains * a.pu * sizeof(unsigned));
+        w.spec.state = reinterpret_cast<double*>(p); p += align256((size_t)a.n_chains * a.pu * SPEC_LANES * (a.d + 3) * sizeof(double));
+        w.spec.Lws = reinterpret_cast<double*>(p);
+    }
     return w;
 }
 
@@ -390,7 +591,9 @@ extern "C" {
 
 int ggp_sizeof_mcmc_args(void) { return (int)sizeof(ggp_mcmc_args); }
 
-long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains)
+}  // extern "C"
+
+long long ggp::workspace_bytes_impl(int m, int d, int pu, int n_chains, bool with_spec)
 {
     if (m <= 0 || d <= 0 || pu <= 0 || n_chains <= 0) return -1;
     const int Mp = round_up32(m);
@@ -401,7 +604,21 @@ long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains)
     b += align256((size_t)n_chains * P * sizeof(int));                             // valid
     b += align256((size_t)n_chains * pu * sizeof(double));                         // sigwl_cand
     b += align256((size_t)n_chains * sizeof(unsigned));                            // per-chain arrival counters
+    if (with_spec) {                                                               // speculative step kernel (few chains)
+        b += align256((size_t)n_chains * pu * 8 * sizeof(double));
+        b += align256((size_t)n_chains * pu * sizeof(unsigned));
+        b += align256((size_t)n_chains * pu * SPEC_LANES * (d + 3) * sizeof(double));
+        b += align256((size_t)n_chains * pu * SPEC_LANES * packed_doubles(Mp) * sizeof(double));
+    }
     return (long long)b;
+}
+
+extern "C" {
+
+long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains)
+{
+    if (m <= 0 || d <= 0 || pu <= 0 || n_chains <= 0) return -1;
+    return workspace_bytes_impl(m, d, pu, n_chains, spec_cluster_size(pu, n_chains, round_up32(m), d) > 0);
 }
 
 int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
@@ -422,7 +639,7 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     }
     if (a.replay) GGP_ARG(a.r_cand && a.r_logacorr && a.r_logu && a.r_valid, "replay tables missing");
     else GGP_ARG(a.uniforms && a.upos && a.n_uniform > 0, "uniform stream missing");
-    const long long need = ggp_mcmc_workspace_bytes(a.m, a.d, a.pu, a.n_chains);
+    const long long need = workspace_bytes_impl(a.m, a.d, a.pu, a.n_chains, false);
     if ((long long)a.workspace_bytes < need) {
         set_error("ggp_mcmc_run_f64: workspace too small (%lld < %lld)", (long long)a.workspace_bytes, need);
         return GGP_ERR_WORKSPACE;
@@ -433,6 +650,7 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     }
     const int Mp = round_up32(a.m);
     int G = choose_cluster((long long)a.pu * a.n_chains, round_up32(a.m));
+    int Gs = 0;                                    // cluster size of the speculative step kernel (0: not used)
     const bool la = (G == 1) && use_lookahead();
     const size_t smem = la ? la_smem_bytes(Mp, a.d) : eval_smem_bytes(Mp, a.d);
     if (smem > 227 * 1024) {
@@ -455,6 +673,30 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         const int rc = deep ? prep(sweep_kernel<true, false, 4>, eval_all_kernel<true, false, 4>)
                             : prep(sweep_kernel<true, false, 2>, eval_all_kernel<true, false, 2>);
         if (rc != GGP_OK) return rc;
+        // speculative step kernel: three clusters per (PC, chain), every one of them resident at the same time
+        if (a.pc_count == 0 && carve_ws(a).spec.Lws != nullptr) Gs = spec_cluster_size(a.pu, a.n_chains, Mp, a.d);
+        if (Gs > 0) {
+            auto prep_spec = [&](auto kern) -> int {
+                GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
+                if (Gs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                    cudaGetLastError(); Gs = 0; return GGP_OK;
+                }
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(SPEC_LANES * a.pu * Gs, a.n_chains); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)Gs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int nact = 0;
+                if (cudaOccupancyMaxActiveClusters(&nact, kern, &cfg) != cudaSuccess || nact < SPEC_LANES * a.pu * a.n_chains) {
+                    cudaGetLastError(); Gs = 0;
+                }
+                return GGP_OK;
+            };
+            const int rs = deep ? prep_spec(sweep_spec_kernel<4>) : prep_spec(sweep_spec_kernel<2>);
+            if (rs != GGP_OK) return rs;
+        }
     } else if (la) {
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GGP_CUDA(cudaFuncSetAttribute(sweep_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cpct));
@@ -485,7 +727,15 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
         else eval_all_kernel<false><<<grid_all, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, mode);
         return cudaGetLastError();
     };
+    const SpecWs specws = wsp.spec;
+    const int rcap = (a.d + 3 + 1) / 2;            // rounds of the speculative kernel per step (arrivals per step: 3 * rcap)
     auto launch_sweep = [&](int t) -> cudaError_t {
+        if (Gs > 0) {
+            const dim3 gs(SPEC_LANES * a.pu * Gs, a.n_chains);
+            const unsigned base = (unsigned)t * (unsigned)rcap;
+            return deep ? launch_maybe_cluster(sweep_spec_kernel<4>, gs, dim3(NT), smem, st, Gs, a, pl, specws, l_stride, sig_cand, arrive, t, base)
+                        : launch_maybe_cluster(sweep_spec_kernel<2>, gs, dim3(NT), smem, st, Gs, a, pl, specws, l_stride, sig_cand, arrive, t, base);
+        }
         if (G > 1) return deep ? launch_maybe_cluster(sweep_kernel<true, false, 4>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, arrive, t)
                                : launch_maybe_cluster(sweep_kernel<true, false, 2>, grid, dim3(NT), smem, st, G, a, pl, Lws, l_stride, sig_cand, arrive, t);
         if (la) sweep_kernel<false, true><<<grid, NT, smem, st>>>(a, pl, Lws, l_stride, sig_cand, arrive, t);
@@ -500,6 +750,7 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     }
     if (a.n_steps > 0) {
         GGP_CUDA(cudaMemsetAsync(arrive, 0, (size_t)a.n_chains * sizeof(unsigned), st));
+        if (Gs > 0) GGP_CUDA(cudaMemsetAsync(specws.cnt, 0, (size_t)a.n_chains * a.pu * sizeof(unsigned), st));
         plan_kernel<<<cb, 32, 0, st>>>(a, pl, 0);
         GGP_CUDA(cudaGetLastError());
     }
@@ -539,7 +790,7 @@ static int check_shard_args(const ggp_mcmc_args* args)
     const ggp_mcmc_args& a = *args;
     GGP_ARG(a.m > 0 && a.d > 0 && a.pu > 0 && a.n_chains > 0, "sizes must be positive");
     GGP_ARG(a.theta && a.sigwl && a.workspace && a.fixed && a.step, "null state / table pointer");
-    GGP_ARG((long long)a.workspace_bytes >= ggp_mcmc_workspace_bytes(a.m, a.d, a.pu, a.n_chains), "workspace too small");
+    GGP_ARG((long long)a.workspace_bytes >= workspace_bytes_impl(a.m, a.d, a.pu, a.n_chains, false), "workspace too small");
     if (a.replay) GGP_ARG(a.r_cand && a.r_logacorr && a.r_logu && a.r_valid, "replay tables missing");
     else GGP_ARG(a.uniforms && a.upos && a.n_uniform > 0, "uniform stream missing");
     return GGP_OK;

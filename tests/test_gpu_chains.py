@@ -93,3 +93,39 @@ def test_pc_sharded_stepping_follows_the_uniform_stream(cuda):
         outs.append({k: o[k].cpu().numpy() for k in ('draws', 'lp', 'accepted', 'consumed')})
     for k in ('draws', 'lp', 'accepted', 'consumed'):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize('spec', ['0', '1'])
+@pytest.mark.parametrize('cfg,chains', [('cfg1', 1), ('cfg1', 2), ('cfg2', 1), ('cfg3', 1)])
+def test_speculative_step_kernel_is_bit_identical(cuda, monkeypatch, cfg, chains, spec):
+    """Few chains: three clusters per (PC, chain) retire two evaluations per round (the second one under both outcomes of
+    the first).  Decisions and draws must be those of the sequential sweep, with the kernel switched off (GGP_SPEC=0) and
+    on; in stream mode the two must also agree with each other bit for bit."""
+    from gladsgp_b200 import ops
+    monkeypatch.setenv('GGP_SPEC', spec)
+    g = np.load(os.path.join(GOLD, 'chain_%s.npz' % cfg))
+    n = min(int(g['n_steps']), 60)
+    gg = {k: (g[k][:n] if k.startswith('rp_') else g[k]) for k in g.files}
+    gg['n_steps'] = np.array(n)
+
+    class G(dict):
+        files = list(gg.keys())
+    out = _replay(G(gg), n_chains=chains)
+    for c in range(chains):
+        assert np.array_equal(out['draws'].cpu().numpy()[:, c, :], g['chain_draws'][:n])
+    assert np.array_equal(out['accepted'].cpu().numpy()[:, 0, :], g['chain_acc'][:n, 0, :])
+    np.testing.assert_allclose(out['lp'].cpu().numpy()[:, 0], g['chain_lp'][:n], rtol=1e-9)
+    # stream mode from the same start: digest of the chain is independent of the kernel choice
+    tb = {k[3:]: g[k] for k in g.files if k.startswith('tb_')}
+    P = tb['theta'].size
+    us = np.random.RandomState(9).random_sample((chains, 2 * P * 25))
+    eng = ops.McmcEngine(g['zt'], np.ascontiguousarray(g['w'].T), g['LamSim'], tb, n_chains=chains)
+    eng.set_state(tb['theta'])
+    o = eng.run(25, tb['step'], uniforms=us, record_accept=True)
+    key = (cfg, chains)
+    cur = (o['draws'].cpu().numpy().tobytes(), o['lp'].cpu().numpy().tobytes(), o['consumed'].cpu().numpy().tobytes())
+    prev = _STREAM_RESULTS.setdefault(key, cur)
+    assert prev == cur
+
+
+_STREAM_RESULTS = {}
