@@ -32,6 +32,7 @@ namespace ggp {
 #ifdef GGP_PHASES
 __device__ unsigned long long g_phase[32];
 __device__ unsigned long long g_phase2[128];     // look-ahead variant: [warp][16] cycles per activity, block 0
+__device__ unsigned long long g_stage[4 * 64 * 2];  // look-ahead variant, block 0: [role][stage][0 = busy, 1 = wait at barrier (E)]
 #define LA_TICK(slot)                                                                       \
     do {                                                                                    \
         if (blockIdx.x == 0 && blockIdx.y == 0) {                                           \
@@ -993,6 +994,9 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
 #endif
 
     for (int jc = 0; jc < nP; ++jc) {
+#ifdef GGP_PHASES
+        const unsigned long long tstage__ = clock64();
+#endif
         const int j = jc - 1;                       // panel finished in this stage (none in stage 0)
         if (j >= 0)                                 // inverse of block j, produced by the previous stage
             for (int idx = tid; idx < 1024; idx += NT) sm.Minv[(idx >> 5) * MI_LD + (idx & 31)] = D[(idx >> 5) * D_LD + (idx & 31)];
@@ -1272,7 +1276,17 @@ static __device__ __forceinline__ double eval_block_loglik_la(const LaSmem& sm, 
             }
         }
         LA_TICK(2);
+#ifdef GGP_PHASES
+        const unsigned long long te0__ = clock64();
+#endif
         __syncthreads();                                                         // (E)
+#ifdef GGP_PHASES
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && jc < 64) {
+            const unsigned long long te1__ = clock64();
+            g_stage[(warp * 64 + jc) * 2 + 0] += te0__ - tstage__;
+            g_stage[(warp * 64 + jc) * 2 + 1] += te1__ - te0__;
+        }
+#endif
         LA_TICK(13);
         if (sm.flag[0] != 0) {
             if (tid == 0 && info) *info = sm.flag[0];

@@ -288,6 +288,14 @@ int ggp_debug_phase_cycles(unsigned long long* out_host, int reset)
     if (reset) GGP_CUDA(cudaMemcpyToSymbol(ggp::g_phase, z, sizeof(z)));
     return GGP_OK;
 }
+int ggp_debug_stage_cycles(unsigned long long* out_host, int reset)
+{
+    static unsigned long long z[4 * 64 * 2];
+    GGP_CUDA(cudaDeviceSynchronize());
+    GGP_CUDA(cudaMemcpyFromSymbol(out_host, ggp::g_stage, sizeof(z)));
+    if (reset) { memset(z, 0, sizeof(z)); GGP_CUDA(cudaMemcpyToSymbol(ggp::g_stage, z, sizeof(z))); }
+    return GGP_OK;
+}
 int ggp_debug_phase2_cycles(unsigned long long* out_host, int reset)
 {
     unsigned long long z[128] = {0};
