@@ -359,8 +359,10 @@ sweep_spec_kernel(ggp_mcmc_args a, Plan pl, SpecWs sw, long long l_stride, doubl
     const int Mp = round_up32(a.m);
     const int G = (int)cluster_nctarank();
     const int cl = blockIdx.x / G;                       // cluster index along x: (PC, lane)
-    const int j = cl / SPEC_LANES, lane_id = cl - j * SPEC_LANES, c = blockIdx.y;
+    const int jl = cl / SPEC_LANES, lane_id = cl - jl * SPEC_LANES, c = blockIdx.y;
+    const int j = a.pc_begin + jl;                       // (PC shard: this launch covers PCs [pc_begin, pc_begin + pc_count))
     const bool lead = (threadIdx.x == 0) && (cluster_ctarank() == 0);
+    const bool shard = a.pc_count > 0;
     const int d = a.d, pu = a.pu, P = d * pu + 2 * pu + 1;
     const int E = d + 3;                                  // evaluations of the PC's sequence (last = lamWOs term)
     double* th = a.theta + (size_t)c * P;
@@ -371,6 +373,11 @@ sweep_spec_kernel(ggp_mcmc_args a, Plan pl, SpecWs sw, long long l_stride, doubl
     const double* wj = chain_w(a, c, j);
     unsigned char* accd = a.accepted ? a.accepted + ((size_t)t * a.n_chains + c) * P : nullptr;
     const double lamwos_cur = th[P - 1];
+    double* xrow = shard ? a.xchg + ((size_t)j * a.n_chains + c) * (2 * d + 6) : nullptr;
+    if (shard && lead && lane_id == 0) {
+        xrow[d + 3] = a.sigwl[(size_t)c * pu + j];
+        for (int e = 0; e < d + 2; ++e) xrow[d + 4 + e] = 0.0;
+    }
     auto site_of = [&](int e) { return e < d ? j * d + e : (e == d ? d * pu + j : (e == d + 1 ? d * pu + pu + j : P - 1)); };
 
     // private state and the list of valid evaluations (identical in the three lanes)
@@ -437,6 +444,7 @@ sweep_spec_kernel(ggp_mcmc_args a, Plan pl, SpecWs sw, long long l_stride, doubl
                 acc0 = pl.logu[o0] < ((l0 - st[d + 2]) + dprior) + pl.lacorr[o0];
                 if (acc0) { st[e0] = c0; st[d + 2] = l0; }
                 if (accd && lane_id == 0) accd[s0] = acc0 ? 1 : 0;
+                if (shard && lane_id == 0) xrow[d + 4 + e0] = acc0 ? 1.0 : 0.0;
             }
             if (e1 >= 0) {
                 const double l1 = acc0 ? l1a : l1r;
@@ -450,6 +458,7 @@ sweep_spec_kernel(ggp_mcmc_args a, Plan pl, SpecWs sw, long long l_stride, doubl
                     const bool acc1 = pl.logu[o1] < ((l1 - st[d + 2]) + dprior) + pl.lacorr[o1];
                     if (acc1) { st[e1] = c1; st[d + 2] = l1; }
                     if (accd && lane_id == 0) accd[s1] = acc1 ? 1 : 0;
+                    if (shard && lane_id == 0) xrow[d + 4 + e1] = acc1 ? 1.0 : 0.0;
                 }
             }
         }
@@ -459,7 +468,10 @@ sweep_spec_kernel(ggp_mcmc_args a, Plan pl, SpecWs sw, long long l_stride, doubl
         // every launch adds the same number of arrivals to the counter, whatever the number of valid evaluations
         const int rcap = (E + 1) >> 1;
         if (nrounds < rcap) atomicAdd(cnt, (unsigned)(rcap - nrounds));
-        if (lane_id == 0) {
+        if (lane_id == 0 && shard) {
+            for (int e = 0; e < d + 3; ++e) xrow[e] = st[e];                     // betaU[:, j], lamUz[j], lamWs[j], SigWl[j]
+            if (pl.valid[(size_t)c * P + (P - 1)]) xrow[d + 3] = sig_cand[(size_t)c * pu + j];
+        } else if (lane_id == 0) {
             for (int e = 0; e < d; ++e) th[j * d + e] = st[e];
             th[d * pu + j] = st[d];
             th[d * pu + pu + j] = st[d + 1];
@@ -573,7 +585,7 @@ static McmcWs carve_ws(const ggp_mcmc_args& a)
     w.arrive = reinterpret_cast<unsigned*>(p);  p += align256((size_t)a.n_chains * sizeof(unsigned));
     w.spec.res = nullptr; w.spec.cnt = nullptr; w.spec.state = nullptr; w.spec.Lws = nullptr;
     // (a workspace sized while the speculative kernel was switched off simply runs without it)
-    if (spec_cluster_size(a.pu, a.n_chains, Mp, a.d) > 0 &&
+    if (spec_cluster_size(1, a.n_chains, Mp, a.d) > 0 &&
         (long long)a.workspace_bytes >= workspace_bytes_impl(a.m, a.d, a.pu, a.n_chains, true)) {
         w.spec.res = reinterpret_cast<double*>(p);   p += align256((size_t)a.n_chains * a.pu * 8 * sizeof(double));
         w.spec.cnt = reinterpret_cast<unsigned*>(p); p += align256((size_t)a.n_chains * a.pu * sizeof(unsigned));
@@ -618,7 +630,8 @@ extern "C" {
 long long ggp_mcmc_workspace_bytes(int m, int d, int pu, int n_chains)
 {
     if (m <= 0 || d <= 0 || pu <= 0 || n_chains <= 0) return -1;
-    return workspace_bytes_impl(m, d, pu, n_chains, spec_cluster_size(pu, n_chains, round_up32(m), d) > 0);
+    // few chains: room for the speculative step kernel (eligible for the whole chain or for a PC shard of it)
+    return workspace_bytes_impl(m, d, pu, n_chains, spec_cluster_size(1, n_chains, round_up32(m), d) > 0);
 }
 
 int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
@@ -674,7 +687,8 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
                             : prep(sweep_kernel<true, false, 2>, eval_all_kernel<true, false, 2>);
         if (rc != GGP_OK) return rc;
         // speculative step kernel: three clusters per (PC, chain), every one of them resident at the same time
-        if (a.pc_count == 0 && carve_ws(a).spec.Lws != nullptr) Gs = spec_cluster_size(a.pu, a.n_chains, Mp, a.d);
+        const int npc = a.pc_count > 0 ? a.pc_count : a.pu;                 // PCs swept by this call
+        if (carve_ws(a).spec.Lws != nullptr) Gs = spec_cluster_size(npc, a.n_chains, Mp, a.d);
         if (Gs > 0) {
             auto prep_spec = [&](auto kern) -> int {
                 GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -683,13 +697,13 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
                     cudaGetLastError(); Gs = 0; return GGP_OK;
                 }
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(SPEC_LANES * a.pu * Gs, a.n_chains); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
+                cfg.gridDim = dim3(SPEC_LANES * npc * Gs, a.n_chains); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = (unsigned)Gs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
                 int nact = 0;
-                if (cudaOccupancyMaxActiveClusters(&nact, kern, &cfg) != cudaSuccess || nact < SPEC_LANES * a.pu * a.n_chains) {
+                if (cudaOccupancyMaxActiveClusters(&nact, kern, &cfg) != cudaSuccess || nact < SPEC_LANES * npc * a.n_chains) {
                     cudaGetLastError(); Gs = 0;
                 }
                 return GGP_OK;
@@ -729,10 +743,10 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     };
     const SpecWs specws = wsp.spec;
     const int rcap = (a.d + 3 + 1) / 2;            // rounds of the speculative kernel per step (arrivals per step: 3 * rcap)
-    auto launch_sweep = [&](int t) -> cudaError_t {
+    auto launch_sweep = [&](int t, int tbase = -1) -> cudaError_t {
         if (Gs > 0) {
-            const dim3 gs(SPEC_LANES * a.pu * Gs, a.n_chains);
-            const unsigned base = (unsigned)t * (unsigned)rcap;
+            const dim3 gs(SPEC_LANES * (a.pc_count > 0 ? a.pc_count : a.pu) * Gs, a.n_chains);
+            const unsigned base = (unsigned)(tbase >= 0 ? tbase : t) * (unsigned)rcap;   // rounds since the counters were zeroed
             return deep ? launch_maybe_cluster(sweep_spec_kernel<4>, gs, dim3(NT), smem, st, Gs, a, pl, specws, l_stride, sig_cand, arrive, t, base)
                         : launch_maybe_cluster(sweep_spec_kernel<2>, gs, dim3(NT), smem, st, Gs, a, pl, specws, l_stride, sig_cand, arrive, t, base);
         }
@@ -745,7 +759,8 @@ int ggp_mcmc_run_f64(const ggp_mcmc_args* args, void* stream)
     if (a.init_sigwl) GGP_CUDA(launch_eval_all(0));
     if (shard) {
         // one step of a PC shard: candidates come from ggp_mcmc_plan_f64 / ggp_mcmc_close_f64, the close is the caller's
-        GGP_CUDA(launch_sweep(a.step_index));
+        if (Gs > 0) GGP_CUDA(cudaMemsetAsync(specws.cnt, 0, (size_t)a.n_chains * a.pu * sizeof(unsigned), st));
+        GGP_CUDA(launch_sweep(a.step_index, 0));
         return GGP_OK;
     }
     if (a.n_steps > 0) {

@@ -57,11 +57,13 @@ def test_many_replicas_of_one_chain_are_identical(cuda):
     assert np.array_equal(out['accepted'].cpu().numpy()[:, 0, :], g['chain_acc'][:steps, 0, :])
 
 
+@pytest.mark.parametrize('spec', ['0', '1'])
 @pytest.mark.parametrize('splits', [[(0, 5)], [(0, 3), (3, 2)], [(0, 2), (2, 2), (4, 1)]])
-def test_pc_sharded_stepping_is_bit_identical(cuda, splits):
+def test_pc_sharded_stepping_is_bit_identical(cuda, monkeypatch, splits, spec):
     """SURVEY 8e ii: the PCs of a chain swept by several shards (here: one after the other on one GPU, standing in for
     the ranks), rows exchanged, step closed from the gathered rows -- same decisions and draws as the one-kernel step."""
     from gladsgp_b200 import ops
+    monkeypatch.setenv('GGP_SPEC', spec)            # shards of a single chain run the speculative step kernel when it fits
     g = np.load(os.path.join(GOLD, 'chain_cfg1.npz'))
     tb = {k[3:]: g[k] for k in g.files if k.startswith('tb_')}
     steps = 40
