@@ -87,14 +87,15 @@ def randomized_svd_sharded(X_slab, p, k=None, q=1, omega_slab=None, products=Non
     for _ in range(q):
         Zt = xty(X_slab, Y)
         Y = allsum(sketch(X_slab, Zt.contiguous()))
-    Q, _ = torch.linalg.qr(Y, mode='reduced')
+    Qd, _ = torch.linalg.qr(Y.double(), mode='reduced')       # FP64 orthonormalisation (see gladsgp_b200/svd.py)
+    Q = Qd.float()
     B = xty(X_slab, Q.contiguous()).double()                  # (r, n_local)
     G = allsum(B @ B.T)
     lam, E = torch.linalg.eigh(G)
     lam = torch.flip(lam, dims=[0]).clamp_min(0.0)
     E = torch.flip(E, dims=[1])
     S = torch.sqrt(lam)
-    U = (Q.double() @ E).float()
+    U = (Qd @ E).float()
     Vh = ((E.T @ B) / S.clamp_min(1e-300)[:, None]).float()
     return U[:, :p], S[:p].float(), Vh[:p]
 
