@@ -13,6 +13,8 @@
 // canonical K-major 128-byte-swizzle layout (the one TMA would write; TMA cannot be used because the row pitch of
 // the reference's ensembles, 4*n_y bytes with n_y = 3693*365, is not a multiple of 16 bytes).  One elected thread of
 // the MMA warp issues tcgen05.mma and signals completion with tcgen05.commit on an mbarrier.
+#include <cuda.h>                 // CUtensorMap and the cuTensorMapEncodeTiled prototype (resolved at run time, no -lcuda)
+#include <cstdlib>
 #include "ggp_common.cuh"
 #include "../../include/gladsgp_b200.h"
 
@@ -108,6 +110,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
 // issue all tcgen05.ld of an epilogue first, then wait once
@@ -348,6 +359,253 @@ sketch_tc_kernel(const float* __restrict__ X, int m, long long n, const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Y = X * Omega with the operand tiles brought in by TMA (cp.async.bulk.tensor, SWIZZLE_128B: the hardware writes the
+// 256 x 32 tile of X and the 32 x 32 tile of Omega^T straight into the K-major 128-byte-swizzle layout the MMA
+// descriptors expect).  Needs a row pitch that is a multiple of 16 bytes (n % 4 == 0) and a 16-byte aligned base; other
+// shapes keep the register-staged kernel above.  Raw stages (written by TMA) and derived stages (written by the splitters):
+//   warp 12     lane 0: per chunk, waits for the stage to be free, arms raw_full[stage] with the byte count and issues the
+//               two tensor copies (out-of-range rows / columns are zero-filled by the hardware)
+//   warps 0-7   splitters: wait for raw_full, turn every 16-byte piece x into tf32(x) (written back in place) and x - tf32(x)
+//               (written to the lo tile at the same swizzled offset), fence.proxy.async, arrive on full[stage]
+//   warps 8-11  MMA issue + epilogue, unchanged
+// The split, the order of the MMAs and the epilogue are those of sketch_tc_kernel: the two kernels give identical bits.
+constexpr int TMA_THREADS = 384 + 32;
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// FUSE: the two products that share the hi tile of X, x_hi o_hi and x_hi o_lo, are ONE MMA with N = 64 (the hi and lo tiles of
+// Omega are adjacent, i.e. rows 0-31 / 32-63 of one K-major operand), x_lo o_hi is a second one with N = 32: 16 instead of 24
+// MMAs per chunk and the X tiles are read from shared memory twice instead of three times.  The three partial sums live in
+// separate TMEM columns and are added in the epilogue (round-to-nearest FP32).
+// RAWHI: the hi tile of X is the raw float32 tile as TMA delivered it -- the tensor core takes the upper 19 bits of each operand
+// element, i.e. tf32(x) by truncation (checked: same accuracy against the float64 product) -- and the splitters only write
+// x - trunc_tf32(x) to the lo tile.
+// Shared memory: a ring of TMA_RAW raw stages [X raw 32 KB | Omega raw 4 KB] that only TMA writes (RAWHI) -- four chunks of
+// prefetch, 108 KB in flight per SM -- and a ring of two derived stages [X lo 32 KB | Omega hi 4 KB | Omega lo 4 KB].
+#ifndef GGP_TMA_BURST
+#define GGP_TMA_BURST 1      // adjacent chunks requested together (2: measured, no gain)
+#endif
+constexpr int TMA_BURST = GGP_TMA_BURST;
+constexpr int TMA_RAW = 4;
+constexpr int TMA_RAW_BYTES = TC_A_BYTES + TC_B_BYTES;            // 36 KB
+constexpr int TMA_LO_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;         // 40 KB
+constexpr int TMA_SMEM_BYTES = TMA_RAW * TMA_RAW_BYTES + 2 * TMA_LO_BYTES;   // 224 KB
+
+template <bool FUSE, bool RAWHI, int DRY = 0>      // DRY (developer timing only, wrong results): 1 = no split, 2 = no split, no MMA
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+sketch_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapO, int m, long long n,
+                  int r, int k0, float* __restrict__ partial)
+{
+    constexpr int DCOLS = FUSE ? 96 : 32;                       // TMEM columns per 128-row tile and buffer
+    constexpr int TCOLS = FUSE ? 512 : TC_TMEM_COLS;            // 2 buffers x 2 tiles x DCOLS, rounded up to a power of two
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t raw_bar[TMA_RAW];          // TMA bytes of a raw stage have landed
+    __shared__ __align__(8) uint64_t rawfree_bar[TMA_RAW];      // MMAs reading a raw stage are done
+    __shared__ __align__(8) uint64_t full_bar[2];               // derived stage written by the splitters
+    __shared__ __align__(8) uint64_t lofree_bar[2];             // MMAs reading a derived stage are done
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ uint32_t tmem_base_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row_base = blockIdx.y * TC_ROWS;
+    unsigned char* lo_base = smem_raw + TMA_RAW * TMA_RAW_BYTES;
+
+    if (tid == 0) {
+        for (int s = 0; s < TMA_RAW; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&rawfree_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 256); mbar_init(&lofree_bar[s], 1); mbar_init(&tmem_full_bar[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    const long long nchunk = (n + TC_K - 1) / TC_K;
+    const long long per = (nchunk + gridDim.x - 1) / gridDim.x;
+    const long long ch_begin = (long long)blockIdx.x * per;
+    const int n_my = (int)(ch_begin >= nchunk ? 0 : (nchunk - ch_begin < per ? nchunk - ch_begin : per));
+
+    if (warp == 12) {
+        // ================= TMA producer (one thread) =================
+        if (lane == 0) {
+            // (TMA_BURST > 1: adjacent chunks requested together -- their 128-byte row pieces are adjacent in memory; no gain measured.
+            //  The pure TMA stream of 256-row x 128-byte boxes, without split and MMA, tops out at 4.0 TB/s = 0.61 of the copy peak.)
+            for (int it0 = 0; it0 < n_my; it0 += TMA_BURST) {
+                const int nb = (n_my - it0 < TMA_BURST) ? n_my - it0 : TMA_BURST;
+                for (int b = 0; b < nb; ++b) {
+                    const int it = it0 + b, s = it % TMA_RAW;
+                    if (it >= TMA_RAW) mbar_wait(&rawfree_bar[s], (uint32_t)((it / TMA_RAW - 1) & 1));
+                }
+                for (int b = 0; b < nb; ++b) {
+                    const int it = it0 + b, s = it % TMA_RAW;
+                    unsigned char* st = smem_raw + (size_t)s * TMA_RAW_BYTES;
+                    const int c0 = (int)((ch_begin + it) * TC_K);
+                    mbar_arrive_expect_tx(&raw_bar[s], (uint32_t)TMA_RAW_BYTES);
+                    tma_load_2d(st, &mapX, c0, row_base, &raw_bar[s]);
+                    tma_load_2d(st + TC_A_BYTES, &mapO, c0, k0, &raw_bar[s]);
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ================= splitters =================
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it % TMA_RAW, l = it & 1;
+            mbar_wait(&raw_bar[s], (uint32_t)((it / TMA_RAW) & 1));
+            if (it >= 2) mbar_wait(&lofree_bar[l], (uint32_t)((it / 2 - 1) & 1));       // MMAs of chunk it-2 done with the slot
+            unsigned char* st = smem_raw + (size_t)s * TMA_RAW_BYTES;
+            unsigned char* lt = lo_base + (size_t)l * TMA_LO_BYTES;
+            if (DRY) { fence_async_smem(); mbar_arrive(&full_bar[l]); continue; }
+            // 2048 16-byte pieces of X per stage, 8 per thread; consecutive threads, consecutive pieces (conflict-free);
+            // hi and lo share the (swizzled) offset, so the swizzle never has to be computed here
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t off = (uint32_t)(u * 256 + tid) * 16u;
+                const uint4 x = *reinterpret_cast<const uint4*>(st + off);
+                uint4 hi, lo;
+                if (RAWHI) {
+                    lo.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(x.x & 0xFFFFE000u));
+                    lo.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(x.y & 0xFFFFE000u));
+                    lo.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(x.z & 0xFFFFE000u));
+                    lo.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(x.w & 0xFFFFE000u));
+                } else {
+                    split_tf32(__uint_as_float(x.x), hi.x, lo.x);
+                    split_tf32(__uint_as_float(x.y), hi.y, lo.y);
+                    split_tf32(__uint_as_float(x.z), hi.z, lo.z);
+                    split_tf32(__uint_as_float(x.w), hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(st + off) = hi;
+                }
+                *reinterpret_cast<uint4*>(lt + off) = lo;
+            }
+            {
+                const uint32_t off = (uint32_t)tid * 16u;                 // 256 pieces of Omega^T: hi and lo both go to the derived stage
+                const uint4 x = *reinterpret_cast<const uint4*>(st + TC_A_BYTES + off);
+                uint4 hi, lo;
+                split_tf32(__uint_as_float(x.x), hi.x, lo.x);
+                split_tf32(__uint_as_float(x.y), hi.y, lo.y);
+                split_tf32(__uint_as_float(x.z), hi.z, lo.z);
+                split_tf32(__uint_as_float(x.w), hi.w, lo.w);
+                *reinterpret_cast<uint4*>(lt + TC_A_BYTES + off) = hi;
+                *reinterpret_cast<uint4*>(lt + TC_A_BYTES + TC_B_BYTES + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(&full_bar[l]);
+        }
+    } else {
+        // ================= MMA issue (warp 8, lane 0) + epilogue (warps 8-11) =================
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
+        constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64);
+        const int ew = warp - 8;
+        const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
+        const uint32_t raw_lo0 = umma_sw128_lo(smem_u32(smem_raw));
+        const uint32_t der_lo0 = umma_sw128_lo(smem_u32(lo_base));
+        float acc[2][32];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[t][c] = 0.f;
+#pragma unroll 1
+        for (int it = 0; it <= n_my; ++it) {
+            if (it < n_my && warp == 8 && lane == 0) {
+                const int s = it % TMA_RAW, l = it & 1;
+                mbar_wait(&full_bar[l], (uint32_t)((it / 2) & 1));
+                tc_fence_after();
+                // descriptor low words: base + (byte offset >> 4); K step: + 2, next M tile: + 1024
+                const uint32_t ah0 = raw_lo0 + (uint32_t)s * (TMA_RAW_BYTES >> 4);
+                const uint32_t al0 = der_lo0 + (uint32_t)l * (TMA_LO_BYTES >> 4);
+                const uint32_t bh0 = al0 + (TC_A_BYTES >> 4);
+                const uint32_t d0 = tmem_base + (uint32_t)((it & 1) * 2 * DCOLS);
+#pragma unroll
+                for (int t = 0; t < (DRY == 2 ? 0 : 4); ++t) {
+                    const uint64_t bh = umma_join(bh0 + 2 * t, UMMA_SW128_HI);          // (FUSE: N = 64 spans the hi and the lo tile)
+                    const uint64_t bl = umma_join(bh0 + (TC_B_BYTES >> 4) + 2 * t, UMMA_SW128_HI);
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const uint64_t ah = umma_join(ah0 + tile * 1024 + 2 * t, UMMA_SW128_HI);
+                        const uint64_t al = umma_join(al0 + tile * 1024 + 2 * t, UMMA_SW128_HI);
+                        const uint32_t d = d0 + tile * DCOLS;
+                        if (FUSE) {
+                            if (t == 0) { umma_tf32<false>(d, ah, bh, idesc64); umma_tf32<false>(d + 64, al, bh, idesc); }
+                            else { umma_tf32<true>(d, ah, bh, idesc64); umma_tf32<true>(d + 64, al, bh, idesc); }
+                        } else {
+                            if (t == 0) umma_tf32<false>(d, al, bh, idesc); else umma_tf32<true>(d, al, bh, idesc);
+                            umma_tf32<true>(d, ah, bl, idesc);
+                            umma_tf32<true>(d, ah, bh, idesc);
+                        }
+                    }
+                }
+                umma_commit(&rawfree_bar[s]);
+                umma_commit(&lofree_bar[l]);
+                umma_commit(&tmem_full_bar[it & 1]);
+            }
+            __syncwarp();
+            if (it >= 1) {
+                const int j = it - 1;
+                mbar_wait(&tmem_full_bar[j & 1], (uint32_t)((j >> 1) & 1));
+                tc_fence_after();
+                const uint32_t tb = tmem_base + t_lane + (uint32_t)((j & 1) * 2 * DCOLS);
+                if (FUSE) {
+                    // per tile: columns [0, 32) x_hi o_hi, [32, 64) x_hi o_lo, [64, 96) x_lo o_hi: small terms first, then the sum
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {                              // 16 columns at a time: register budget
+                            uint32_t vh[16], vl[16], vx[16];
+                            tmem_ld16(tb + tile * DCOLS + 16 * h, vh);
+                            tmem_ld16(tb + tile * DCOLS + 32 + 16 * h, vl);
+                            tmem_ld16(tb + tile * DCOLS + 64 + 16 * h, vx);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                acc[tile][16 * h + c] += (__uint_as_float(vl[c]) + __uint_as_float(vx[c])) + __uint_as_float(vh[c]);
+                        }
+                } else {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(tb, v0);
+                    tmem_ld32(tb + 32, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[0][c] += __uint_as_float(v0[c]);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[1][c] += __uint_as_float(v1[c]);
+                }
+                tc_fence_before();
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+            const int row = row_base + tile * 128 + 32 * ew + lane;
+            if (row < m) {
+                float4* out = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * m + row) * 32);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    out[c] = make_float4(acc[tile][4 * c], acc[tile][4 * c + 1], acc[tile][4 * c + 2], acc[tile][4 * c + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+    }
+}
+
 // ---- A operand from tensor memory (tcgen05.mma "TS" form): lanes = M rows, one 32-bit column per K element ----
 template <bool ACC>
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc)
@@ -568,6 +826,44 @@ __global__ void tc_reduce_kernel(const float* __restrict__ partial, int nparts, 
     Y[(size_t)row * r + k0 + k] = (float)s;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder()
+{
+    static tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tmap_encode_fn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// row-major float32 [rows][cols] (pitch = cols), box = box_rows x 32 columns, 128-byte swizzle, zero fill outside
+static bool make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows)
+{
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_K, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    // L2 promotion: a 128-byte row piece pulls its 256-byte neighbourhood into L2 -- the other half is the same CTA's next chunk
+    // (GGP_TMA_L2=128 / 256, developer experiments)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("GGP_TMA_L2")) promo = (atoi(e) == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int tc_sm_count()
 {
     int dev = 0, sms = 148;
@@ -606,6 +902,26 @@ int ggp_rsvd_sketch_tc_f32(const float* X, int m, long long n, const float* Omeg
     if (gx > nchunk) gx = nchunk;
     const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES;
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    // TMA-fed kernel: pitch a multiple of 16 bytes, 16-byte aligned bases, coordinates within int32 (GGP_TMA=0 switches it off)
+    const char* env_tma = getenv("GGP_TMA");
+    bool tma = vec && ((reinterpret_cast<uintptr_t>(OmegaT) & 15) == 0) && n < (1LL << 31) && !(env_tma && atoi(env_tma) == 0);
+    CUtensorMap mapX, mapO;
+    if (tma) tma = make_tmap_f32(&mapX, X, m, n, TC_ROWS) && make_tmap_f32(&mapO, OmegaT, r, n, 32);
+    if (tma) {
+        // GGP_TMA: 1 = same split and MMA order as the register-staged kernel (identical bits); 2 = fused hi products;
+        // 3 (default) = fused products + raw hi tile
+        const int mode = env_tma ? atoi(env_tma) : 3;
+        auto kern = (mode == 1) ? sketch_tma_kernel<false, false> : (mode == 2) ? sketch_tma_kernel<true, false> :
+                    (mode == 8) ? sketch_tma_kernel<true, true, 1> : (mode == 9) ? sketch_tma_kernel<true, true, 2> : sketch_tma_kernel<true, true>;
+        GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+        for (int k0 = 0; k0 < r; k0 += 32) {
+            kern<<<dim3((unsigned)gx, gy), TMA_THREADS, TMA_SMEM_BYTES, st>>>(mapX, mapO, m, n, r, k0, partial);
+            GGP_CUDA(cudaGetLastError());
+            tc_reduce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(partial, (int)gx, m, r, k0, Y_out);
+            GGP_CUDA(cudaGetLastError());
+        }
+        return GGP_OK;
+    }
     GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GGP_CUDA(cudaFuncSetAttribute(sketch_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int k0 = 0; k0 < r; k0 += 32) {

@@ -78,3 +78,42 @@ def test_sharded_rsvd_single_rank_equals_randomized_svd(cuda):
     np.testing.assert_array_equal(S.cpu().numpy(), S0)
     np.testing.assert_array_equal(U.cpu().numpy(), U0)
     np.testing.assert_array_equal(Vh.cpu().numpy(), Vh0)
+
+
+@pytest.mark.parametrize('m,n,r', [(256, 4096, 25), (512, 20004, 25), (700, 9000, 40), (100, 5004, 25), (33, 260, 3)])
+def test_tma_fed_sketch_equals_register_staged_sketch(cuda, monkeypatch, m, n, r):
+    """Row pitch a multiple of 16 bytes: the sketch pass takes its operand tiles through TMA (cp.async.bulk.tensor, 128-byte
+    swizzle).  Split, MMA order and epilogue are those of the register-staged kernel, so the two give identical bits --
+    including ragged last chunks and row blocks (zero fill by the hardware instead of by predicated loads)."""
+    import torch
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(m + n)
+    X = (rng.standard_normal((m, n)) * rng.uniform(0.1, 3, size=(1, n))).astype(np.float32)
+    Om = rng.standard_normal((r, n)).astype(np.float32)
+    Xd, Od = torch.as_tensor(X, device='cuda'), torch.as_tensor(Om, device='cuda')
+    monkeypatch.setenv('GGP_TMA', '0')
+    ref = ops.rsvd_sketch_tc(Xd, Od).cpu().numpy()
+    monkeypatch.setenv('GGP_TMA', '1')
+    got = ops.rsvd_sketch_tc(Xd, Od).cpu().numpy()
+    assert np.array_equal(got, ref)
+    truth = X.astype(np.float64) @ Om.astype(np.float64).T
+    assert np.abs(got - truth).max() <= 1e-6 * np.abs(truth).max()
+
+
+@pytest.mark.parametrize('mode', ['2', '3'])
+@pytest.mark.parametrize('m,n,r', [(512, 20004, 25), (700, 9000, 40), (100, 5004, 25)])
+def test_tma_sketch_fused_products_and_raw_hi_tile(cuda, monkeypatch, mode, m, n, r):
+    """GGP_TMA=2: x_hi o_hi and x_hi o_lo as one N = 64 MMA, the three partial sums added in the epilogue; GGP_TMA=3 (default):
+    additionally the hi tile of X is the raw float32 tile (the tensor core truncates to TF32) and only x - trunc(x) is written.
+    Both stay at FP32-level accuracy against the float64 product and are deterministic."""
+    import torch
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(m + n + 1)
+    X = (rng.standard_normal((m, n)) * rng.uniform(0.1, 3, size=(1, n))).astype(np.float32)
+    Om = rng.standard_normal((r, n)).astype(np.float32)
+    Xd, Od = torch.as_tensor(X, device='cuda'), torch.as_tensor(Om, device='cuda')
+    monkeypatch.setenv('GGP_TMA', mode)
+    got = ops.rsvd_sketch_tc(Xd, Od).cpu().numpy()
+    truth = X.astype(np.float64) @ Om.astype(np.float64).T
+    assert np.abs(got - truth).max() <= 1e-6 * np.abs(truth).max()
+    assert np.array_equal(got, ops.rsvd_sketch_tc(Xd, Od).cpu().numpy())
