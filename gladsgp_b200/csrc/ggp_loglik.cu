@@ -135,6 +135,96 @@ cov_build_kernel(const double* __restrict__ X, int m, int d, const double* __res
     }
 }
 
+// Row-block version (round 2) for m a multiple of 64 and a 16-byte aligned output: one CTA per (64-row block bi, matrix)
+// walks the tiles bj = 0 .. bi of its block.  Per CTA, not per tile: the exponential table, sqrt(beta) and the row side of the
+// distance product; the column side of the next tile is staged (two warps) while the current tile is computed.  The tile's own
+// copy AND its mirror image leave straight from the accumulator fragments (streaming stores: 64 contiguous bytes per row and
+// instruction either way; no tile in shared memory, one barrier per tile); the diagonal rule is applied in the diagonal tile alone.  Same arithmetic
+// per entry as cov_build_kernel: identical bits.  (A two-level-table exponential with the scale folded into the exponent, 9 instead
+// of 14 FP64 operations per entry, made this kernel slower: 0.356 vs 0.333 ms -- the second table lookup costs more than the operations.)
+template <int KSC>
+__global__ void __launch_bounds__(256, 4)
+cov_build_rows_kernel(const double* __restrict__ X, int m, int d, const double* __restrict__ beta,
+                      const double* __restrict__ lamz, const double* __restrict__ diag_add, double* __restrict__ C)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int KS = KSC > 0 ? KSC : cov_ksteps(d), K4 = 4 * KS;
+    double* XA = reinterpret_cast<double*>(smem_raw);      // [CT][K4] row side:    [x~, |x~|^2, 1, 0..]
+    double* XB = XA + CT * K4;                             // [2][CT][K4] column side: [2 x~, -1, -|x~|^2, 0..] (double-buffered)
+    double* etab = XB + 2 * CT * K4;                       // [32]
+    double* sbs = etab + 32;                               // [d] sqrt(beta)
+    const int b = blockIdx.y;
+    const int bi = (int)gridDim.x - 1 - (int)blockIdx.x;   // long row blocks first
+    const double* be = beta + (size_t)b * d;
+    const double il = 1.0 / lamz[b];
+    const double dg = il + diag_add[b];
+    const int r0 = bi * CT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    fill_exp_table(etab);
+    if (tid >= 128 && tid < 128 + d) sbs[tid - 128] = sqrt(be[tid - 128]);
+    __syncthreads();
+    // coordinates of 64 points -> one side of the distance product (thread lr of a 64-thread group)
+    auto stage = [&](double* dst0, int p0, bool colside, int lr) {
+        double* dst = dst0 + lr * K4;
+        double rr = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double x = __ldg(X + (size_t)(p0 + lr) * d + k) * sbs[k];
+            rr = fma(x, x, rr);
+            dst[k] = colside ? 2.0 * x : x;
+        }
+        for (int k = d + 2; k < K4; ++k) dst[k] = 0.0;
+        dst[d] = colside ? -1.0 : rr;
+        dst[d + 1] = colside ? -rr : 1.0;
+    };
+    if (tid < CT) stage(XA, r0, false, tid);
+    else if (tid < 2 * CT) stage(XB, 0, true, tid - CT);
+    __syncthreads();
+    double* Cb = C + (size_t)b * m * m;
+    const int lr = 8 * warp + g;
+    for (int bj = 0; bj <= bi; ++bj) {
+        const int c0 = bj * CT;
+        const double* XBc = XB + (bj & 1) * CT * K4;
+        // column side of the next tile (warps 4 and 5; visible after the barrier at the end of this iteration)
+        if (bj < bi && tid >= 2 * CT && tid < 3 * CT) stage(XB + ((bj + 1) & 1) * CT * K4, c0 + CT, true, tid - 2 * CT);
+        double dn[8][2];
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) { dn[cb][0] = 0.0; dn[cb][1] = 0.0; }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const double a = XA[lr * K4 + 4 * s + q];
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) dmma884(dn[cb][0], dn[cb][1], a, XBc[(8 * cb + g) * K4 + 4 * s + q]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) dn[cb][e] = exp_neg(dn[cb][e], etab) * il;
+        if (bj == bi) {                                      // diagonal tile: complete (both triangles), no mirror image
+            const int dcol = lr - 2 * q;
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (dcol == 8 * cb + e) dn[cb][e] = dg;
+        }
+        double* drow = Cb + (size_t)(r0 + lr) * m + c0 + 2 * q;
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) __stcs(reinterpret_cast<double2*>(drow + 8 * cb), make_double2(dn[cb][0], dn[cb][1]));
+        if (bj != bi) {
+            // mirror image, also straight from the fragments: entry (row g, column 2q + e) of an 8 x 8 block goes to output row
+            // c0 + 8 cb + 2q + e, column r0 + 8 warp + g -- per store instruction the eight lanes with the same q write 64
+            // contiguous bytes, the same segment size as the tile's own copy; no transposition through shared memory
+            double* dt = Cb + (size_t)(c0 + 2 * q) * m + r0 + lr;
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) {
+                __stcs(dt + (size_t)(8 * cb) * m, dn[cb][0]);
+                __stcs(dt + (size_t)(8 * cb + 1) * m, dn[cb][1]);
+            }
+        }
+        __syncthreads();                                     // the next tile's column side is in place
+    }
+}
+
 // SepiaDistCov type 2: S21[b][i][t] = exp(-sum_k beta_k (x_ik - xp_tk)^2) / lamz, (m x n) row-major.
 __global__ void __launch_bounds__(256)
 cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__ Xp, int n, int d,
@@ -254,6 +344,27 @@ int ggp_cov_build_f64(const double* X, int m, int d, const double* beta, const d
         GGP_CUDA(cudaGetLastError());
         return GGP_OK;
     };
+    // whole 64-row blocks and an aligned output: the row-block kernel (GGP_COVROWS=0 keeps the tile kernel)
+    const char* env_rows = getenv("GGP_COVROWS");
+    if (m % CT == 0 && (reinterpret_cast<uintptr_t>(C_out) & 15) == 0 && !(env_rows && atoi(env_rows) == 0)) {
+        const size_t smem_r = (size_t)(3 * CT * 4 * cov_ksteps(d) + 32 + d) * sizeof(double);
+        auto run_rows = [&](auto kern) -> int {
+            GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            kern<<<dim3(nt, B), 256, smem_r, st>>>(X, m, d, beta, lamz, diag_add, C_out);
+            GGP_CUDA(cudaGetLastError());
+            return GGP_OK;
+        };
+        if (smem_r <= 200 * 1024) {
+            switch (cov_ksteps(d)) {
+                case 1: return run_rows(cov_build_rows_kernel<1>);
+                case 2: return run_rows(cov_build_rows_kernel<2>);
+                case 3: return run_rows(cov_build_rows_kernel<3>);
+                case 4: return run_rows(cov_build_rows_kernel<4>);
+                case 5: return run_rows(cov_build_rows_kernel<5>);
+                default: return run_rows(cov_build_rows_kernel<0>);
+            }
+        }
+    }
     switch (cov_ksteps(d)) {
         case 1: return run(cov_build_kernel<1>);
         case 2: return run(cov_build_kernel<2>);
