@@ -226,43 +226,83 @@ cov_build_rows_kernel(const double* __restrict__ X, int m, int d, const double* 
 }
 
 // SepiaDistCov type 2: S21[b][i][t] = exp(-sum_k beta_k (x_ik - xp_tk)^2) / lamz, (m x n) row-major.
-__global__ void __launch_bounds__(256)
+// Round 2: same scheme as the row-block covariance build -- 64 x 64 tile per CTA, squared distances as the rank-(d+2) DMMA
+// product (row side from X, column side from Xp), exp_neg fused, the tile stored straight from the accumulator fragments
+// (64 contiguous bytes per row and store instruction) -- instead of scalar difference sums and libm exp per entry.
+template <int KSC>
+__global__ void __launch_bounds__(256, 4)
 cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__ Xp, int n, int d,
                  const double* __restrict__ beta, const double* __restrict__ lamz,
-                 double* __restrict__ S21)
+                 double* __restrict__ S21, int n_ct, int n_rt, int ct_per_cta)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* Sr = reinterpret_cast<double*>(smem_raw);      // [CT][d]
-    double* Sc = Sr + CT * d;                              // [CT][d]
-    const int b = blockIdx.z;
-    const int r0 = blockIdx.y * CT, c0 = blockIdx.x * CT;
+    const int KS = KSC > 0 ? KSC : cov_ksteps(d), K4 = 4 * KS;
+    double* XA = reinterpret_cast<double*>(smem_raw);      // [CT][K4] row side:    [x~, |x~|^2, 1, 0..]
+    double* XB = XA + CT * K4;                             // [2][CT][K4] column side: [2 x~, -1, -|x~|^2, 0..] (double-buffered)
+    double* etab = XB + 2 * CT * K4;                       // [32]
+    double* sbs = etab + 32;                               // [d]
+    // CTA = (matrix b, 64-row block, run of ct_per_cta column tiles): prologue and row side once per CTA
+    const int runs = (n_ct + ct_per_cta - 1) / ct_per_cta;
+    const int per_b = n_rt * runs;
+    const int b = blockIdx.x / per_b;
+    const int tix = blockIdx.x - b * per_b;
+    const int r0 = (tix / runs) * CT;
+    const int ct0 = (tix % runs) * ct_per_cta, ct1 = min(n_ct, ct0 + ct_per_cta);
     const double* be = beta + (size_t)b * d;
     const double il = 1.0 / lamz[b];
-    for (int idx = threadIdx.x; idx < CT * d; idx += blockDim.x) {
-        int r = idx / d, k = idx - r * d;
-        double sb = sqrt(be[k]);
-        Sr[idx] = (r0 + r < m) ? X[(size_t)(r0 + r) * d + k] * sb : 0.0;
-        Sc[idx] = (c0 + r < n) ? Xp[(size_t)(c0 + r) * d + k] * sb : 0.0;
-    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    fill_exp_table(etab);
+    if (tid >= 128 && tid < 128 + d) sbs[tid - 128] = sqrt(be[tid - 128]);
     __syncthreads();
-    double* Sb = S21 + (size_t)b * m * n;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    for (int rr = 0; rr < 4; ++rr) {
-        const int lr = ty + 16 * rr;
-        const int r = r0 + lr;
-        if (r >= m) continue;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int lc = 4 * tx + cc;
-            const int c = c0 + lc;
-            if (c >= n) continue;
-            double dist = 0.0;
-            for (int k = 0; k < d; ++k) {
-                double df = Sr[lr * d + k] - Sc[lc * d + k];
-                dist = fma(df, df, dist);
-            }
-            Sb[(size_t)r * n + c] = exp(-dist) * il;
+    auto stage = [&](double* dst0, const double* P, int p0, int np, bool colside, int lr) {
+        const bool in = p0 + lr < np;
+        const double* src = P + (size_t)(in ? p0 + lr : 0) * d;
+        double* dst = dst0 + lr * K4;
+        double rr = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double x = in ? __ldg(src + k) * sbs[k] : 0.0;
+            rr = fma(x, x, rr);
+            dst[k] = colside ? 2.0 * x : x;
         }
+        for (int k = d; k < K4; ++k) dst[k] = 0.0;
+        if (in) {
+            dst[d] = colside ? -1.0 : rr;
+            dst[d + 1] = colside ? -rr : 1.0;
+        }
+    };
+    if (tid < CT) stage(XA, X, r0, m, false, tid);
+    else if (tid < 2 * CT) stage(XB + (ct0 & 1) * CT * K4, Xp, ct0 * CT, n, true, tid - CT);
+    __syncthreads();
+    const int lr = 8 * warp + g;
+    const int r = r0 + lr;
+    double* Sb = S21 + (size_t)b * m * n;
+    const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(S21) & 15) == 0);
+    for (int ct = ct0; ct < ct1; ++ct) {
+        const int c0 = ct * CT;
+        const double* XBc = XB + (ct & 1) * CT * K4;
+        if (ct + 1 < ct1 && tid >= 2 * CT && tid < 3 * CT) stage(XB + ((ct + 1) & 1) * CT * K4, Xp, c0 + CT, n, true, tid - 2 * CT);
+        double dn[8][2];
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) { dn[cb][0] = 0.0; dn[cb][1] = 0.0; }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const double a = XA[lr * K4 + 4 * s + q];
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) dmma884(dn[cb][0], dn[cb][1], a, XBc[(8 * cb + g) * K4 + 4 * s + q]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {
+            const double v0 = exp_neg(dn[cb][0], etab) * il, v1 = exp_neg(dn[cb][1], etab) * il;
+            const int c = c0 + 8 * cb + 2 * q;
+            if (r < m) {
+                if (vec2 && c + 1 < n) __stcs(reinterpret_cast<double2*>(Sb + (size_t)r * n + c), make_double2(v0, v1));
+                else {
+                    if (c < n) Sb[(size_t)r * n + c] = v0;
+                    if (c + 1 < n) Sb[(size_t)r * n + c + 1] = v1;
+                }
+            }
+        }
+        __syncthreads();                                     // the next tile's column side is in place
     }
 }
 
@@ -381,13 +421,28 @@ int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, co
     GGP_ARG(X && Xp && beta && lamz && S21_out, "null pointer");
     GGP_ARG(m > 0 && n > 0 && d > 0 && B > 0, "m, n, d, B must be positive");
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = (size_t)(2 * CT * d) * sizeof(double);
+    const size_t smem = (size_t)(3 * CT * 4 * cov_ksteps(d) + 32 + d) * sizeof(double);
     GGP_ARG(smem <= 200 * 1024, "d too large for cross_cov");
-    GGP_CUDA(cudaFuncSetAttribute(cross_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((n + CT - 1) / CT, (m + CT - 1) / CT, B);
-    cross_cov_kernel<<<grid, 256, smem, st>>>(X, m, Xp, n, d, beta, lamz, S21_out);
-    GGP_CUDA(cudaGetLastError());
-    return GGP_OK;
+    const int n_ct = (n + CT - 1) / CT, n_rt = (m + CT - 1) / CT;
+    // runs of up to 8 column tiles per CTA (prologue and row side amortised), but at least ~4 CTAs per SM slot in total
+    int ct_per_cta = 8;
+    while (ct_per_cta > 1 && (long long)n_rt * B * ((n_ct + ct_per_cta - 1) / ct_per_cta) < 4LL * 592) ct_per_cta >>= 1;
+    const long long nblk = (long long)n_rt * B * ((n_ct + ct_per_cta - 1) / ct_per_cta);
+    GGP_ARG(nblk < (1LL << 31), "B * tiles(m, n) must be below 2^31 CTAs");
+    auto run = [&](auto kern) -> int {
+        GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)nblk, 256, smem, st>>>(X, m, Xp, n, d, beta, lamz, S21_out, n_ct, n_rt, ct_per_cta);
+        GGP_CUDA(cudaGetLastError());
+        return GGP_OK;
+    };
+    switch (cov_ksteps(d)) {
+        case 1: return run(cross_cov_kernel<1>);
+        case 2: return run(cross_cov_kernel<2>);
+        case 3: return run(cross_cov_kernel<3>);
+        case 4: return run(cross_cov_kernel<4>);
+        case 5: return run(cross_cov_kernel<5>);
+        default: return run(cross_cov_kernel<0>);
+    }
 }
 
 #ifdef GGP_PHASES

@@ -27,4 +27,10 @@ for mode in ('0', '1'):
     res['covrows' + mode] = dict(ms=ms, gbs=B * m * m * 8 / ms / 1e6, frac=B * m * m * 8 / ms / 1e6 / 6533.8)
 res['identical'] = bool(torch.equal(outs['0'], outs['1']))
 res['symmetric'] = bool(torch.equal(outs['1'], outs['1'].transpose(1, 2)))
+n = 4096
+tp = synthetic.test_design(n, q)
+Xp = torch.as_tensor(np.concatenate([0.5 * np.ones((n, 1)), tp.astype(np.float64)], axis=1), device='cuda')
+Bc = 64
+ms = ev(lambda: ops.cross_cov(Xd, Xp, bd[:Bc], ld[:Bc]))
+res['cross_cov'] = dict(ms=ms, gbs=Bc * m * n * 8 / ms / 1e6, frac=Bc * m * n * 8 / ms / 1e6 / 6533.8)
 print(json.dumps(res))
