@@ -402,6 +402,14 @@ constexpr int TMA_RAW_BYTES = TC_A_BYTES + TC_B_BYTES;            // 36 KB
 constexpr int TMA_LO_BYTES = TC_A_BYTES + 2 * TC_B_BYTES;         // 40 KB
 constexpr int TMA_SMEM_BYTES = TMA_RAW * TMA_RAW_BYTES + 2 * TMA_LO_BYTES;   // 224 KB
 
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 template <bool FUSE, bool RAWHI, int DRY = 0>      // DRY (developer timing only, wrong results): 1 = no split, 2 = no split, no MMA
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 sketch_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapO, int m, long long n,
@@ -813,6 +821,203 @@ xty_ts_kernel(const float* __restrict__ X, int m, long long n, const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bt = Y^T X with TMA-fed operand tiles (row pitch of X a multiple of 16 bytes).  The output column block (256 columns = two
+// M = 128 tiles) is the MMA's M dimension and the m rows are K:  D[c][k] = sum_i X[i][c] Y[i][k].  X is row-major, i.e.
+// contiguous along M: the A operand is MN-major, whose one legal layout for 32-bit elements is the "128-byte swizzle with
+// 32-byte atoms" (32 consecutive columns of one row per 128-byte line, the 32-byte unit u of line k at position u ^ (k % 4);
+// blocks of 32 columns 4096 bytes apart) -- exactly what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B from a box of
+// 32 columns x 32 rows.  A chunk is eight such boxes side by side: 32 rows x 1 KB contiguous per row.  Y^T (r x m, a few KB,
+// transposed once by a small kernel) is the K-major B operand as Omega^T is in the sketch pass.  Raw / derived rings, splitters,
+// fused hi products and epilogue accumulation as in sketch_tma_kernel; a CTA walks down the rows of its column block in 32-row
+// chunks and writes the block of Bt after the last one.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
+}
+
+__global__ void transpose_pad_kernel(const float* __restrict__ Y, int m, int r, float* __restrict__ Yt, int pitch)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;               // Yt[k][i], k < r, i < pitch (zero beyond m)
+    if (idx >= r * pitch) return;
+    const int k = idx / pitch, i = idx - k * pitch;
+    Yt[idx] = (i < m) ? Y[(size_t)i * r + k] : 0.f;
+}
+
+// BOX3 (n a multiple of 32): X is described to TMA as a 3-D tensor {32 columns, m rows, n / 32 column blocks} (strides 4 n and 128
+// bytes), so that ONE box {32, 32, 8} brings the eight 32 x 32 blocks of a chunk in block-major order -- nine copies per chunk
+// were what bounded the 2-D version (1.15 ms against 0.95 for the register -> TMEM kernel).
+template <bool BOX3, int DRY = 0>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+xty_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int m, long long n,
+               int r, int k0, float* __restrict__ Bt)
+{
+    constexpr int DCOLS = 96;
+    constexpr int TCOLS = 512;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t raw_bar[TMA_RAW];
+    __shared__ __align__(8) uint64_t rawfree_bar[TMA_RAW];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ __align__(8) uint64_t lofree_bar[2];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ uint32_t tmem_base_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* lo_base = smem_raw + TMA_RAW * TMA_RAW_BYTES;
+
+    if (tid == 0) {
+        for (int s = 0; s < TMA_RAW; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&rawfree_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 256); mbar_init(&lofree_bar[s], 1); mbar_init(&tmem_full_bar[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    const int nk = (m + 31) / 32;                                           // K chunks per column block
+    const long long nblk = (n + TC_ROWS - 1) / TC_ROWS;                     // column blocks of 256
+    const int blk_my = (blockIdx.x < nblk) ? (int)((nblk - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+    const int n_my = blk_my * nk;
+    auto blk_col = [&](int b) { return ((long long)blockIdx.x + (long long)b * gridDim.x) * TC_ROWS; };
+
+    if (warp == 12) {
+        if (lane == 0) {
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it % TMA_RAW;
+                if (it >= TMA_RAW) mbar_wait(&rawfree_bar[s], (uint32_t)((it / TMA_RAW - 1) & 1));
+                unsigned char* st = smem_raw + (size_t)s * TMA_RAW_BYTES;
+                const int b = it / nk, kc = it - b * nk;
+                const int c0 = (int)blk_col(b), i0 = kc * 32;
+                mbar_arrive_expect_tx(&raw_bar[s], (uint32_t)TMA_RAW_BYTES);
+                if (BOX3) tma_load_3d(st, &mapX, 0, i0, c0 >> 5, &raw_bar[s]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) tma_load_2d(st + j * 4096, &mapX, c0 + 32 * j, i0, &raw_bar[s]);
+                }
+                tma_load_2d(st + TC_A_BYTES, &mapY, i0, k0, &raw_bar[s]);
+            }
+        }
+    } else if (warp < 8) {
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it % TMA_RAW, l = it & 1;
+            mbar_wait(&raw_bar[s], (uint32_t)((it / TMA_RAW) & 1));
+            if (it >= 2) mbar_wait(&lofree_bar[l], (uint32_t)((it / 2 - 1) & 1));
+            unsigned char* st = smem_raw + (size_t)s * TMA_RAW_BYTES;
+            unsigned char* lt = lo_base + (size_t)l * TMA_LO_BYTES;
+            if (DRY) { fence_async_smem(); mbar_arrive(&full_bar[l]); continue; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {                                   // X: raw tile = hi operand, lo = x - trunc_tf32(x)
+                const uint32_t off = (uint32_t)(u * 256 + tid) * 16u;
+                const uint4 x = *reinterpret_cast<const uint4*>(st + off);
+                uint4 lo;
+                lo.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(x.x & 0xFFFFE000u));
+                lo.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(x.y & 0xFFFFE000u));
+                lo.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(x.z & 0xFFFFE000u));
+                lo.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(x.w & 0xFFFFE000u));
+                *reinterpret_cast<uint4*>(lt + off) = lo;
+            }
+            {
+                const uint32_t off = (uint32_t)tid * 16u;                   // Y^T: hi and lo to the derived stage
+                const uint4 x = *reinterpret_cast<const uint4*>(st + TC_A_BYTES + off);
+                uint4 hi, lo;
+                split_tf32(__uint_as_float(x.x), hi.x, lo.x);
+                split_tf32(__uint_as_float(x.y), hi.y, lo.y);
+                split_tf32(__uint_as_float(x.z), hi.z, lo.z);
+                split_tf32(__uint_as_float(x.w), hi.w, lo.w);
+                *reinterpret_cast<uint4*>(lt + TC_A_BYTES + off) = hi;
+                *reinterpret_cast<uint4*>(lt + TC_A_BYTES + TC_B_BYTES + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(&full_bar[l]);
+        }
+    } else {
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 32) | (1u << 15);       // A is MN-major
+        constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64) | (1u << 15);
+        const int ew = warp - 8;
+        const uint32_t t_lane = (uint32_t)(32 * ew) << 16;
+        const uint32_t der_lo0 = umma_sw128_lo(smem_u32(lo_base));
+        float acc[2][32];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[t][c] = 0.f;
+#pragma unroll 1
+        for (int it = 0; it <= n_my; ++it) {
+            if (it < n_my && warp == 8 && lane == 0) {
+                const int s = it % TMA_RAW, l = it & 1;
+                mbar_wait(&full_bar[l], (uint32_t)((it / 2) & 1));
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TMA_RAW_BYTES);
+                const uint32_t a_lo = smem_u32(lo_base + (size_t)l * TMA_LO_BYTES);
+                const uint32_t bh0 = der_lo0 + (uint32_t)l * (TMA_LO_BYTES >> 4) + (TC_A_BYTES >> 4);
+                const uint32_t d0 = tmem_base + (uint32_t)((it & 1) * 2 * DCOLS);
+#pragma unroll
+                for (int t = 0; t < (DRY == 2 ? 0 : 4); ++t) {
+                    const uint64_t bh = umma_join(bh0 + 2 * t, UMMA_SW128_HI);          // N = 64 spans the hi and the lo tile of Y^T
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const uint64_t ah = umma_desc_mn_sw128_32b(a_hi + tile * 16384 + t * 1024, 4096, 512);
+                        const uint64_t al = umma_desc_mn_sw128_32b(a_lo + tile * 16384 + t * 1024, 4096, 512);
+                        const uint32_t d = d0 + tile * DCOLS;
+                        if (t == 0) { umma_tf32<false>(d, ah, bh, idesc64); umma_tf32<false>(d + 64, al, bh, idesc); }
+                        else { umma_tf32<true>(d, ah, bh, idesc64); umma_tf32<true>(d + 64, al, bh, idesc); }
+                    }
+                }
+                umma_commit(&rawfree_bar[s]);
+                umma_commit(&lofree_bar[l]);
+                umma_commit(&tmem_full_bar[it & 1]);
+            }
+            __syncwarp();
+            if (it >= 1) {
+                const int j = it - 1;
+                mbar_wait(&tmem_full_bar[j & 1], (uint32_t)((j >> 1) & 1));
+                tc_fence_after();
+                const uint32_t tb = tmem_base + t_lane + (uint32_t)((j & 1) * 2 * DCOLS);
+#pragma unroll
+                for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t vh[16], vl[16], vx[16];
+                        tmem_ld16(tb + tile * DCOLS + 16 * h, vh);
+                        tmem_ld16(tb + tile * DCOLS + 32 + 16 * h, vl);
+                        tmem_ld16(tb + tile * DCOLS + 64 + 16 * h, vx);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            acc[tile][16 * h + c] += (__uint_as_float(vl[c]) + __uint_as_float(vx[c])) + __uint_as_float(vh[c]);
+                    }
+                tc_fence_before();
+                if ((j + 1) % nk == 0) {
+                    // last chunk of a column block: write Bt[k0 + c][col] and restart the sums
+                    const long long c0 = blk_col(j / nk);
+#pragma unroll
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const long long col = c0 + tile * 128 + 32 * ew + lane;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (col < n && k0 + c < r) __stcs(Bt + (size_t)(k0 + c) * n + col, acc[tile][c]);
+                            acc[tile][c] = 0.f;
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+    }
+}
+
 // fixed-order FP64 sum of the per-CTA partials [nparts][m][32] -> Y[m][r] columns k0 .. k0+31
 __global__ void tc_reduce_kernel(const float* __restrict__ partial, int nparts, int m, int r, int k0,
                                  float* __restrict__ Y)
@@ -847,12 +1052,13 @@ static tmap_encode_fn tmap_encoder()
     return fn;
 }
 // row-major float32 [rows][cols] (pitch = cols), box = box_rows x 32 columns, 128-byte swizzle, zero fill outside
-static bool make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows)
+static bool make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows,
+                          long long pitch = 0, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B)
 {
     tmap_encode_fn enc = tmap_encoder();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint64_t strides[1] = {(cuuint64_t)(pitch > 0 ? pitch : cols) * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)TC_K, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     // L2 promotion: a 128-byte row piece pulls its 256-byte neighbourhood into L2 -- the other half is the same CTA's next chunk
@@ -860,7 +1066,7 @@ static bool make_tmap_f32(CUtensorMap* map, const float* base, long long rows, l
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (const char* e = getenv("GGP_TMA_L2")) promo = (atoi(e) == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -942,6 +1148,45 @@ int ggp_rsvd_xty_tc_f32(const float* X, int m, long long n, const float* Y, int 
     const long long nblk = (n + TC_ROWS - 1) / TC_ROWS;
     long long gx = tc_sm_count();
     if (gx > nblk) gx = nblk;
+    // TMA-fed kernel (pitch of X a multiple of 16 bytes, aligned base): OFF by default, GGP_TMA_XTY=1 selects it.  Measured at cfg3
+    // size: 1.09-1.15 ms against 0.95 ms for the register -> TMEM kernel below; with split and MMA switched off its pure TMA stream
+    // (256 lines of 128 bytes per chunk, as one 3-D box or as eight 2-D boxes) runs at 3.3 TB/s -- the same ~9 cycles per 128-byte
+    // line per SM that bound the sketch pass's stream at 4.0 TB/s.  Kept as a tested, documented negative result.
+    const char* env_tma = getenv("GGP_TMA_XTY");
+    bool tma = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && n < (1LL << 31) && (env_tma && atoi(env_tma) != 0);
+    if (tma) {
+        const int pitch = (m + 3) & ~3;
+        float* Yt = nullptr;
+        if (cudaMallocAsync(reinterpret_cast<void**>(&Yt), (size_t)r * pitch * sizeof(float), st) != cudaSuccess) { cudaGetLastError(); tma = false; }
+        CUtensorMap mapX, mapY;
+        const bool box3 = (n % 32 == 0);
+        if (tma && box3) {
+            tmap_encode_fn enc = tmap_encoder();
+            const cuuint64_t dims[3] = {32, (cuuint64_t)m, (cuuint64_t)(n / 32)};
+            const cuuint64_t strides[2] = {(cuuint64_t)n * sizeof(float), 32 * sizeof(float)};
+            const cuuint32_t box[3] = {32, 32, 8};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            tma = enc && enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        } else if (tma) {
+            tma = make_tmap_f32(&mapX, X, m, n, 32, 0, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        }
+        if (tma) tma = make_tmap_f32(&mapY, Yt, r, m, 32, pitch);
+        if (tma) {
+            transpose_pad_kernel<<<(r * pitch + 255) / 256, 256, 0, st>>>(Y, m, r, Yt, pitch);
+            const int mode = atoi(env_tma);             // 1 = the kernel; 8 / 9 = dry modes (developer timing only, wrong results)
+            auto kern = !box3 ? xty_tma_kernel<false> : (mode == 8) ? xty_tma_kernel<true, 1> : (mode == 9) ? xty_tma_kernel<true, 2> : xty_tma_kernel<true>;
+            GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+            for (int k0 = 0; k0 < r; k0 += 32) {
+                kern<<<(unsigned)gx, TMA_THREADS, TMA_SMEM_BYTES, st>>>(mapX, mapY, m, n, r, k0, Bt_out);
+                GGP_CUDA(cudaGetLastError());
+            }
+            GGP_CUDA(cudaFreeAsync(Yt, st));
+            return GGP_OK;
+        }
+        if (Yt) cudaFreeAsync(Yt, st);
+    }
     for (int k0 = 0; k0 < r; k0 += 32) {
         xty_ts_kernel<<<(unsigned)gx, TC_THREADS, 0, st>>>(X, m, n, Y, r, k0, Bt_out);
         GGP_CUDA(cudaGetLastError());

@@ -117,3 +117,25 @@ def test_tma_sketch_fused_products_and_raw_hi_tile(cuda, monkeypatch, mode, m, n
     truth = X.astype(np.float64) @ Om.astype(np.float64).T
     assert np.abs(got - truth).max() <= 1e-6 * np.abs(truth).max()
     assert np.array_equal(got, ops.rsvd_sketch_tc(Xd, Od).cpu().numpy())
+
+
+@pytest.mark.parametrize('m,n,r', [(512, 20004, 25), (700, 9000, 40), (100, 5004, 25), (33, 260, 3), (256, 4096, 25),
+                                   (512, 20032, 25), (300, 8224, 40), (70, 320, 5)])      # last three: n % 32 == 0, one 3-D box per chunk
+def test_tma_fed_xty_matches_float64_and_tmem_kernel(cuda, monkeypatch, m, n, r):
+    """Y^T X with the X tiles brought in by TMA in the MN-major 128-byte / 32-byte-atom swizzle layout: FP32-level accuracy
+    against the float64 product, agreement with the register -> TMEM kernel (GGP_TMA=0) at the same level, deterministic."""
+    import torch
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(m + n + 2)
+    X = (rng.standard_normal((m, n)) * rng.uniform(0.1, 3, size=(1, n))).astype(np.float32)
+    Yh = rng.standard_normal((m, r)).astype(np.float32)
+    Xd, Yd = torch.as_tensor(X, device='cuda'), torch.as_tensor(Yh, device='cuda')
+    truth = Yh.astype(np.float64).T @ X.astype(np.float64)
+    monkeypatch.setenv('GGP_TMA_XTY', '0')
+    ref = ops.rsvd_xty_tc(Xd, Yd).cpu().numpy()
+    monkeypatch.setenv('GGP_TMA_XTY', '1')             # (off by default: slower than the register -> TMEM kernel, see csrc)
+    got = ops.rsvd_xty_tc(Xd, Yd).cpu().numpy()
+    assert got.shape == (r, n)
+    assert np.abs(got - truth).max() <= 1e-6 * np.abs(truth).max()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(truth).max()
+    assert np.array_equal(got, ops.rsvd_xty_tc(Xd, Yd).cpu().numpy())

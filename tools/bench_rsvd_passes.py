@@ -24,8 +24,10 @@ for tma in ('0', '1', '2', '3', '8', '9'):
 x1 = X.view(-1)
 ms = ev(lambda: x1.sum())
 res['torch_sum_read_only'] = dict(ms=ms, gbs=4.0 * m * n / ms / 1e6)
-ms = ev(lambda: ops.rsvd_xty_tc(X, Y))
-res['xty'] = dict(ms=ms, gbs=4.0 * m * n / ms / 1e6, frac=4.0 * m * n / ms / 1e6 / 6533.8)
+for tma in ('0', '1', '8', '9'):
+    os.environ['GGP_TMA_XTY'] = tma
+    ms = ev(lambda: ops.rsvd_xty_tc(X, Y))
+    res['xty_tma' + tma] = dict(ms=ms, gbs=4.0 * m * n / ms / 1e6, frac=4.0 * m * n / ms / 1e6 / 6533.8)
 ref = X.double()[:, :200000] @ omT.double()[:, :200000].T
 for tma in ('0', '3'):
     os.environ['GGP_TMA'] = tma
