@@ -295,6 +295,16 @@ def prediction_bench(torch, model, args, rank, world):
     for i in range(E2E_CALLS):
         pe = SepiaEmulatorPrediction(t_pred=tp[i * n_call:(i + 1) * n_call], samples=samples, model=model)
     e2e_s = time.perf_counter() - t0
+    # the same joint work, device-timed with resident inputs (the e2e number's own ceiling): predict with V, joint covariance,
+    # Cholesky draw
+    xj = xp[:n_call].contiguous()
+    zj = torch.randn(ns * PU, n_call, dtype=torch.float64, device='cuda')
+
+    def joint_pass():
+        mj, vj, Vj = P1.predict(xj, want_V=True)
+        Sj = P1.pred_cov(xj, Vj)
+        return ops.chol_draw(Sj, zj)
+    joint_ms = _ev_ms(torch, joint_pass)
     # reconstruction of a batch of fields (get_y), float32
     w32 = pe.w[:, :4, :].astype(np.float32).reshape(-1, PU)
     sd_ = model.data.sim_data
@@ -305,10 +315,10 @@ def prediction_bench(torch, model, args, rank, world):
     r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
     r0.record(); ops.reconstruct(wd, Kd, sdd, mud, out=out); r1.record(); torch.cuda.synchronize()
     rec_ms = r0.elapsed_time(r1)
-    t = torch.tensor([fac_ms, prd_ms, e2e_s * 1e3, rec_ms], dtype=torch.float64, device='cuda')
+    t = torch.tensor([fac_ms, prd_ms, e2e_s * 1e3, rec_ms, joint_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    fac_ms, prd_ms, e2e_ms, rec_ms = [float(x) for x in t.cpu()]
+    fac_ms, prd_ms, e2e_ms, rec_ms, joint_ms = [float(x) for x in t.cpu()]
     n_y = int(Kd.shape[1])
     res = {
         'metric': 'emulator_preds_per_s', 'unit': '(sample,design) pairs/s, all pu PCs',
@@ -317,6 +327,9 @@ def prediction_bench(torch, model, args, rank, world):
         'value_pc_space_incl_factorisation': nsamp * npred * world / ((prd_ms + fac_ms) * 1e-3),
         'factor_ms': fac_ms, 'predict_ms': prd_ms,
         'predict_tflops_fp64': nsamp * PU * npred * (M * M + (3 * D + 2) * M) / (prd_ms * 1e-3) / 1e12,
+        'value_joint_256': nsamp * n_call * world / (joint_ms * 1e-3),
+        'joint_256_note': 'device-timed, resident inputs: one call of 256 designs with the joint covariance and the Cholesky draw '
+                          '(predict_kernel + pred_cov_kernel + chol_draw_kernel), the work the e2e figure below includes',
         'e2e': {'value': nsamp * n_call * E2E_CALLS * world / (e2e_ms * 1e-3),
                 'api': 'SepiaEmulatorPrediction(t_pred=256 designs, samples, model), %d calls, default (joint) behaviour' % E2E_CALLS,
                 'note': 'host numpy in; joint covariance per (sample, PC), one realisation per sample from the global np.random '

@@ -589,7 +589,10 @@ static __device__ __forceinline__ void fill_panel_coords(double* __restrict__ SC
 // of w lives in global memory.  Only CTA 0 returns the value.
 // RA: register ring depth of the A fragments in the pair GEMM (cluster kernels, 168 registers per thread: 4 for matrices up
 // to 1024 rows -- single-chain cfg3 +5 % -- and 2 above, where the deeper ring measured 10 % slower)
-template <bool CL = false, int RA = GGP_RA>
+// SRC = 1 (one CTA per matrix only): the matrix is GIVEN -- X points to a symmetric m x m row-major array instead of
+// coordinates (d = 0, beta unused) -- and the vector step is a product instead of a solve: u_out[0:m] = L w (the
+// multivariate-normal draw of the prediction path, ggp_chol_draw_f64).  The factorisation arithmetic is the same code.
+template <bool CL = false, int RA = GGP_RA, int SRC = 0>
 static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, const double* __restrict__ X, int m, int Mp, int d,
                                     const double* beta, double lamz, double diag_add,
                                     const double* __restrict__ w, double* __restrict__ Lp,
@@ -611,7 +614,8 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
     if (CL) cluster_sync_all();   // previous evaluation (and the caller's state update) finished cluster-wide
     __syncthreads();   // previous user of the shared buffers is done
     if (tid < d) sm.sb[tid] = sqrt(beta[tid]);
-    for (int r = crank * NT + tid; r < Mp; r += G * NT) wres[r] = (r < m) ? w[r] : 0.0;
+    static_assert(!(CL && SRC != 0), "given-matrix mode runs one CTA per matrix");
+    for (int r = crank * NT + tid; r < Mp; r += G * NT) wres[r] = (SRC == 0 && r < m) ? w[r] : 0.0;
     if (CL && crank == 0 && tid == 0) aux[Mp + 32] = 0.0;
     fill_exp_table(sm.etab);
     fill_slab_offsets(sm.soff, Mp);
@@ -633,7 +637,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
         const int nmy = (nunits - gw + TW - 1) / TW;
         const int npairs = max(1, (nmy + 1) >> 1);          // every warp runs pair 0 (it holds the barriers)
         if (CL) cluster_sync_all();                          // panel j-1 (factor rows, wres) visible cluster-wide
-        fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
+        if constexpr (SRC == 0) fill_panel_coords(sm.SC, X, sm.sb, d, m, row0);
         __syncthreads();
         GGP_TICK(0);
         double* __restrict__ scr = LT + warp * 512;          // per-warp scratch of the covariance step (LT and D are idle then)
@@ -664,11 +668,27 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
             }
             GGP_TICKW(2, 20, acc[0][0][0] + acc[1][3][1] + acc[0][3][1] + acc[1][0][0]);
             // ------------------------------------------------------------------ 2. covariance, P = C - S (registers)
-            {
+            if constexpr (SRC == 0) {
                 const int rr[2] = {rb[0] + g, rb[1] + g};
                 const bool ok[2] = {rr[0] < m, rr[1] < m};
                 if (nu == 2) pair_cov<2>(acc, X, rr, ok, sm.SC, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane);
                 else if (nu == 1) pair_cov<1>(acc, X, rr, ok, sm.SC, sm.sb, d, m, row0, q, inv_lamz, diag, true, sm.etab, scr, lane);
+            } else {
+                // entries of the given matrix (identity in the padding rows and columns)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i < nu) {
+                        const int r = rb[i] + g;
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = row0 + 8 * cb + 2 * q + e;
+                                const double v = (r < m && c < m) ? __ldg(X + (size_t)r * m + c) : ((r == c) ? 1.0 : 0.0);
+                                acc[i][cb][e] = v - acc[i][cb][e];
+                            }
+                    }
+                }
             }
             GGP_TICKW(2, 21, acc[0][0][0] + acc[1][3][1]);
 
@@ -744,10 +764,11 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                     return -INFINITY;
                 }
                 if (warp == 0 && !failed) {
+                    double myu = 0.0;
+                    if constexpr (SRC == 0) {
                     // forward solve of the w block: u = Ljj^-1 wres[row0 : row0+32]
                     double b = wres[row0 + lane];
                     GGP_TICKW(0, 11, b);
-                    double myu = 0.0;
 #pragma unroll 1
                     for (int c = 0; c < 32; ++c) {
                         const double uc = __shfl_sync(0xffffffffu, b, c) * sm.rdiag[c];
@@ -758,6 +779,15 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                     if (CL) aux[Mp + lane] = myu;
                     quad += myu * myu;
                     if (u_out) u_out[row0 + lane] = myu;
+                    } else {
+                    // product step: (L w)[row0 + lane] = earlier panels (wres) + the diagonal block's row (zeros above the diagonal)
+                    sm.uj[lane] = (row0 + lane < m) ? w[row0 + lane] : 0.0;
+                    __syncwarp();
+                    double b = wres[row0 + lane];
+#pragma unroll 4
+                    for (int c = 0; c < 32; ++c) b = fma(D[lane * D_LD + c], sm.uj[c], b);
+                    if (row0 + lane < m) u_out[row0 + lane] = b;
+                    }
                     // store the diagonal rows of L (zeros above the diagonal)
 #pragma unroll 1
                     for (int ks = 0; ks < 4; ++ks) {
@@ -846,7 +876,7 @@ static __device__ __forceinline__ double eval_block_loglik(const EvalSmem& sm, c
                     double sdot = s0 + s1;
                     sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
                     sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-                    if (q == 0) wres[r] -= sdot;
+                    if (q == 0) wres[r] -= (SRC == 0) ? sdot : -sdot;
                     GGP_TICKW(2, 22, sdot);
                 }
             }

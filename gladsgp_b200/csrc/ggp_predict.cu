@@ -473,11 +473,61 @@ static int launch_reconstruct(const float* w, const float* K, const float* sd, i
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multivariate-normal deviate of a (sample, PC) block from its joint predictive covariance: dev = L z, Sigma = L L^T.
+// One CTA per block; the factorisation is eval_block_loglik's (DMMA left-looking panels, packed factor as scratch) with
+// the matrix entries read from memory instead of generated, and a product in place of the forward solve.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, GGP_CTAS_PER_SM)
+chol_draw_kernel(const double* __restrict__ Sigma, int n, int Mp, const double* __restrict__ z, double* __restrict__ Lws,
+                 long long l_stride, double* __restrict__ dev, int* __restrict__ info, int b0)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t b = (size_t)b0 + blockIdx.x;
+    EvalSmem sm = carve_eval_smem(smem_raw, Mp, 0);
+    eval_block_loglik<false, GGP_RA, 1>(sm, Sigma + b * n * n, n, Mp, 0, nullptr, 1.0, 0.0, z + b * n,
+                                        Lws + (size_t)blockIdx.x * l_stride, dev + b * n, info + b);
+}
+
 }  // namespace ggp
 
 using namespace ggp;
 
 extern "C" {
+
+long long ggp_chol_draw_workspace_bytes(int n, int B)
+{
+    if (n <= 0 || B <= 0) return -1;
+    return (long long)B * packed_doubles(round_up32(n)) * (long long)sizeof(double);
+}
+
+int ggp_chol_draw_f64(const double* Sigma, int n, int B, const double* z, double* dev_out, int* info_out,
+                      void* workspace, long long workspace_bytes, void* stream)
+{
+    GGP_ARG(Sigma && z && dev_out && info_out && workspace, "null pointer");
+    GGP_ARG(n > 0 && B > 0, "n, B must be positive");
+    const int Mp = round_up32(n);
+    const size_t smem = eval_smem_bytes(Mp, 0);
+    if (smem > 227 * 1024) {
+        set_error("ggp_chol_draw_f64: n=%d needs %zu B of shared memory (> 227 KB)", n, smem);
+        return GGP_ERR_UNSUPPORTED;
+    }
+    const long long per = ggp_chol_draw_workspace_bytes(n, 1);
+    const long long chunk = workspace_bytes / per;            // blocks whose scratch factor fits the workspace
+    if (chunk < 1) {
+        set_error("ggp_chol_draw_f64: workspace too small (%lld < %lld for one block)", workspace_bytes, per);
+        return GGP_ERR_WORKSPACE;
+    }
+    GGP_CUDA(cudaFuncSetAttribute(chol_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GGP_CUDA(cudaFuncSetAttribute(chol_draw_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, eval_carveout_pct(smem)));
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (int)((B - b0 < chunk) ? B - b0 : chunk);
+        chol_draw_kernel<<<nb, NT, smem, (cudaStream_t)stream>>>(Sigma, n, Mp, z, reinterpret_cast<double*>(workspace),
+                                                                 packed_doubles(Mp), dev_out, info_out, (int)b0);
+        GGP_CUDA(cudaGetLastError());
+    }
+    return GGP_OK;
+}
 
 static int predict_grid(int B, int n)
 {

@@ -326,6 +326,27 @@ class Predictor:
         return Sig
 
 
+CHOL_DRAW_WS_BYTES = 1 << 30         # scratch factors of chol_draw: at most 1 GiB, more blocks go in several launches
+
+
+def chol_draw(Sigma, z):
+    """One multivariate-normal deviate per block: Sigma (B,n,n) f64 symmetric, z (B,n) -> (L z (B,n), info (B,) int32) with
+    Sigma = L L^T (the draw step of SEPIA's wPred; info[b] != 0: block b is not positive definite, its row is undefined)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    B, n = int(Sigma.shape[0]), int(Sigma.shape[-1])
+    assert Sigma.is_cuda and Sigma.dtype == torch.float64 and Sigma.is_contiguous() and tuple(Sigma.shape) == (B, n, n)
+    z = z.to(device='cuda', dtype=torch.float64).contiguous().reshape(B, n)
+    out = torch.empty((B, n), dtype=torch.float64, device='cuda')
+    info = torch.empty((B,), dtype=torch.int32, device='cuda')
+    need = int(lib.ggp_chol_draw_workspace_bytes(n, B))
+    one = int(lib.ggp_chol_draw_workspace_bytes(n, 1))
+    nbytes = max(one, min(need, CHOL_DRAW_WS_BYTES))
+    ws = torch.empty((nbytes // 8,), dtype=torch.float64, device='cuda')
+    check(lib.ggp_chol_draw_f64(ptr(Sigma), n, B, ptr(z), ptr(out), ptr(info), ptr(ws), nbytes, stream_ptr()), 'ggp_chol_draw_f64')
+    return out, info
+
+
 def reconstruct(w, K, sd, mean, out=None):
     """get_y: w (R,pu) f32, K (pu,n_y) f32, sd/mean scalar or (n_y,) -> y (R,n_y) f32 on the device."""
     torch = _lib.require_cuda()

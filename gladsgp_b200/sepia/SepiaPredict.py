@@ -146,12 +146,18 @@ class SepiaEmulatorPrediction(SepiaPrediction):
                           'predictive distributions (no cross-design covariance); pass joint=True for SEPIA\'s joint draw or '
                           'split the designs into smaller calls' % (npred, MAX_JOINT), RuntimeWarning, stacklevel=3)
         joint = self.joint if self.joint is not None else (npred <= MAX_JOINT)
+        # the designs go up once, through a page-locked buffer: a pageable copy issued between the two launches below would
+        # hold the host until the first kernel has finished, and the np.random draws further down would start that much later
+        xh = np.ascontiguousarray(self.xpredt, dtype=np.float64)
+        xst = _pinned(self._pred, 'xp', xh.size)
+        xst.copy_(torch.from_numpy(xh.reshape(-1)))
+        xpd = xst.to('cuda', non_blocking=True).reshape(xh.shape)
         if joint and npred > 1:
-            mean, var, V = self._pred.predict(self.xpredt, want_V=True)
-            Sig = self._pred.pred_cov(self.xpredt, V)                 # (B, n, n)
+            mean, var, V = self._pred.predict(xpd, want_V=True)
+            Sig = self._pred.pred_cov(xpd, V)                         # (B, n, n)
             del V
         else:
-            mean, var = self._pred.predict(self.xpredt)
+            mean, var = self._pred.predict(xpd)
             Sig = None
         self.launches = 2 + (1 if Sig is not None else 0)
         mean = mean.reshape(ns, pu, npred)
@@ -174,21 +180,27 @@ class SepiaEmulatorPrediction(SepiaPrediction):
             if Sig is not None:
                 # realisation = mean + F z with F F^T = Sigma.  Sigma >= I / lamWs is positive definite, so the factor is a
                 # Cholesky factor (SEPIA uses U sqrt(s) of an SVD: the same distribution; neither is bit-comparable across
-                # implementations); the eigen-factor stays as the fall-back for a block cuSOLVER rejects
-                S4 = Sig.reshape(ns, pu, npred, npred)
-                L, info = torch.linalg.cholesky_ex(S4)
-                if bool((info != 0).any().item()):
-                    lam, Qm = torch.linalg.eigh(S4)
-                    dev = torch.einsum('spij,spj->spi', Qm, torch.sqrt(torch.clamp(lam, min=0.0)) * zd)
-                else:
-                    dev = torch.matmul(L, zd.unsqueeze(-1)).squeeze(-1)
+                # implementations); the eigen-factor stays as the fall-back when a block is rejected (info != 0)
+                dev, info = ops.chol_draw(Sig, zd.reshape(ns * pu, npred))
+                dev = dev.reshape(ns, pu, npred)
+                self.launches += 1
+                bad = _pinned(eng, 'bad', 1)
+                bad.copy_((info != 0).any().to(torch.float64).reshape(1), non_blocking=True)
             else:
                 dev = torch.sqrt(torch.clamp(var.reshape(ns, pu, npred), min=0.0)) * zd
+                bad = None
             w = (mean + dev).permute(0, 2, 1).contiguous()           # (ns, npred, pu)
             out = _pinned(eng, 'w', w.numel())
             out.copy_(w.reshape(-1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            if bad is not None and float(bad[0]) != 0.0:
+                lam, Qm = torch.linalg.eigh(Sig.reshape(ns, pu, npred, npred))
+                dev = torch.einsum('spij,spj->spi', Qm, torch.sqrt(torch.clamp(lam, min=0.0)) * zd)
+                out.copy_((mean + dev).permute(0, 2, 1).contiguous().reshape(-1))
+                torch.cuda.current_stream().synchronize()
             self.w = out.numpy().reshape(ns, npred, pu).copy()
+        else:
+            torch.cuda.current_stream().synchronize()                # the staging buffers are reused by the next call
 
     # ------------------------------------------------------------------ outputs
     def get_w(self):

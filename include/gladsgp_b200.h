@@ -157,6 +157,16 @@ int ggp_predict_f64(const double* X, int m, int d, const double* factor, const d
  *   Sigma[b] = S11[b] - V[b] V[b]^T,  S11 off-diagonal = cov(xp_s, xp_t), diagonal = s11_diag[b]. */
 int ggp_pred_cov_f64(const double* Xp, int n, int d, const double* beta, const double* lamz,
                      const double* s11_diag, const double* V, int m, int B, double* Sigma_out, void* stream);
+/* The draw step of SEPIA's wPred (rmultnormsvd on the per-PC blocks of Syhat): one multivariate-normal
+ * deviate per block, dev_out[b] = L[b] z[b] with Sigma[b] = L[b] L[b]^T.  SEPIA multiplies by U sqrt(s) of an SVD; the
+ * Cholesky factor gives the same distribution (neither is bit-comparable across implementations).
+ *   Sigma (B, n, n) row-major symmetric (as written by ggp_pred_cov_f64), z and dev_out (B, n), info_out (B):
+ *   0 or the 1-based index of a non-positive pivot (dev_out[b] is then undefined; the caller falls back).
+ * workspace: scratch factors; any size >= ggp_chol_draw_workspace_bytes(n, 1) works (blocks are processed in as many
+ * launches as the workspace requires), ggp_chol_draw_workspace_bytes(n, B) gives one launch. */
+long long ggp_chol_draw_workspace_bytes(int n, int B);
+int ggp_chol_draw_f64(const double* Sigma, int n, int B, const double* z, double* dev_out, int* info_out,
+                      void* workspace, long long workspace_bytes, void* stream);
 
 /* SepiaEmulatorPrediction.get_y (assess_all_models.py:492), float32:
  *   y[r][c] = (sum_p w[r][p] K[p][c]) * sd[c] + mean[c],  r < R (= nsamp*npred), c < n_y.

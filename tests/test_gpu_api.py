@@ -108,6 +108,28 @@ def test_realisations_have_the_right_distribution(cuda):
     np.testing.assert_allclose(emp_cov, Sig, atol=0.15 * np.outer(sd, sd).max())
 
 
+def test_joint_realisation_is_mean_plus_cholesky_factor_times_the_numpy_draws(cuda):
+    """pred.w with the default joint draw: with the global stream seeded, the realisation is mu + L z for the SAME
+    np.random.normal values SEPIA consumes (one vector of npred*pu values per sample, in sample order), L the Cholesky
+    factor of the per-PC block of Sigma (ggp_chol_draw_f64)."""
+    from sepia.SepiaPredict import SepiaEmulatorPrediction
+    pr = make_problem(m=64, q=3, pu=2)
+    data, model = _build(pr, 3)
+    samples = synthetic.posterior_samples(5, 4, 2, seed=3)
+    tp = synthetic.test_design(6, 3)
+    np.random.seed(99)
+    preds = SepiaEmulatorPrediction(t_pred=tp, samples=samples, model=model, storeMuSigma=True)
+    mu, sigma = preds.get_mu_sigma()
+    ns, npred, pu = preds.w.shape
+    np.random.seed(99)
+    z = np.random.normal(size=ns * npred * pu).reshape(ns, pu, npred)
+    for s in range(ns):
+        for j in range(pu):
+            sl = slice(j * npred, (j + 1) * npred)
+            L = np.linalg.cholesky(sigma[s, sl, sl])
+            np.testing.assert_allclose(preds.w[s, :, j], mu[s, sl] + L @ z[s, j], rtol=1e-9, atol=1e-11)
+
+
 def test_scalar_model_api(cuda):
     """fit_scalar_models.py:45-47,471-483 pattern (pu = 1, default priors, scalar standardisation)."""
     from sepia.SepiaData import SepiaData

@@ -180,3 +180,44 @@ def test_get_y_error_stats_api(cuda):
         np.testing.assert_allclose(got[k], ref[k], rtol=5e-5, err_msg=k)
     assert np.all(np.abs(got['frac_covered'] - ref['frac_covered']) <= 4.0 / y_test.shape[1])
     assert abs(got['integrated_ci'] - ref['integrated_ci']) <= 5e-5 * abs(ref['integrated_ci'])
+
+
+@pytest.mark.parametrize('n,B', [(1, 3), (4, 7), (31, 5), (32, 5), (33, 5), (100, 6), (256, 9), (300, 3)])
+def test_chol_draw_matches_numpy_cholesky(cuda, n, B):
+    """dev = L z with Sigma = L L^T (the draw step of wPred) against numpy.linalg.cholesky, over block sizes around the
+    32-wide panels; entries of a Cholesky factor are unique, so the product must agree to rounding."""
+    import torch
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(n * 100 + B)
+    A = rng.standard_normal((B, n, n + 3))
+    Sig = A @ A.transpose(0, 2, 1) / n + 0.05 * np.eye(n)[None]
+    z = rng.standard_normal((B, n))
+    ref = np.einsum('bij,bj->bi', np.linalg.cholesky(Sig), z)
+    dev, info = ops.chol_draw(torch.as_tensor(Sig, device='cuda'), torch.as_tensor(z, device='cuda'))
+    assert not info.any().item()
+    np.testing.assert_allclose(dev.cpu().numpy(), ref, rtol=1e-10, atol=1e-12)
+
+
+def test_chol_draw_chunked_workspace_and_rejection(cuda, monkeypatch):
+    """A workspace smaller than B scratch factors gives the same result in several launches; a block that is not positive
+    definite is reported in info and leaves the other blocks untouched."""
+    import torch
+    from gladsgp_b200 import ops
+    rng = np.random.default_rng(5)
+    n, B = 96, 11
+    A = rng.standard_normal((B, n, n))
+    Sig = A @ A.transpose(0, 2, 1) / n + 0.1 * np.eye(n)[None]
+    Sig[4] -= 3.0 * np.eye(n)                      # indefinite
+    z = rng.standard_normal((B, n))
+    Sd, zd = torch.as_tensor(Sig, device='cuda'), torch.as_tensor(z, device='cuda')
+    dev1, info1 = ops.chol_draw(Sd, zd)
+    one = int(ops._lib.load().ggp_chol_draw_workspace_bytes(n, 1))
+    monkeypatch.setattr(ops, 'CHOL_DRAW_WS_BYTES', 3 * one + 8)          # 3 blocks per launch
+    dev2, info2 = ops.chol_draw(Sd, zd)
+    i1 = info1.cpu().numpy()
+    assert i1[4] > 0 and not np.delete(i1, 4).any()
+    assert np.array_equal(i1, info2.cpu().numpy())
+    good = np.delete(np.arange(B), 4)
+    assert np.array_equal(dev1.cpu().numpy()[good], dev2.cpu().numpy()[good])
+    ref = np.einsum('bij,bj->bi', np.linalg.cholesky(Sig[good]), z[good])
+    np.testing.assert_allclose(dev1.cpu().numpy()[good], ref, rtol=1e-10, atol=1e-12)

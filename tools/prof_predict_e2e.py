@@ -42,6 +42,8 @@ S4 = Sig.reshape(nsamp, 10, npred, npred)
 res['cholesky_ex_ms'], (L, info) = ev(lambda: torch.linalg.cholesky_ex(S4))
 z = torch.randn(nsamp, 10, npred, dtype=torch.float64, device='cuda')
 res['matmul_ms'], _ = ev(lambda: torch.matmul(L, z.unsqueeze(-1)))
+res['chol_draw_ms'], (dev, inf2) = ev(lambda: ops.chol_draw(Sig, z.reshape(nsamp * 10, npred)))     # what the class runs
+res['chol_draw_max_abs_diff_vs_torch'] = float((dev.reshape(nsamp, 10, npred) - torch.matmul(L, z.unsqueeze(-1)).squeeze(-1)).abs().max())
 t0 = time.perf_counter(); zz = np.random.normal(size=nsamp * 10 * npred); res['host_normal_ms'] = (time.perf_counter() - t0) * 1e3
 t0 = time.perf_counter(); k = __import__('gladsgp_b200.sepia.SepiaPredict', fromlist=['x'])._samples_key(samples, model, False); res['samples_key_ms'] = (time.perf_counter() - t0) * 1e3
 res['pairs_per_call'] = nsamp * npred
