@@ -404,7 +404,7 @@ def rsvd_bench(torch, data, svd_s):
     peak, src = measured_peaks()
     byt = 4.0 * m * n
     return {'m': int(m), 'n_y': int(n), 'rank': r, 'randomized_svd_s': svd_s,
-            'sketch_pass': {'kernel': 'ggp::sketch_tc_kernel (Y = X Omega, tcgen05 3xTF32)', 'ms': sk, 'gbs': byt / sk / 1e6,
+            'sketch_pass': {'kernel': 'ggp::sketch_tma_kernel (Y = X Omega, tcgen05 3xTF32, X tiles by TMA; GGP_TMA=0: ggp::sketch_tc_kernel)' if os.environ.get('GGP_TMA', '3') != '0' else 'ggp::sketch_tc_kernel (Y = X Omega, tcgen05 3xTF32)', 'ms': sk, 'gbs': byt / sk / 1e6,
                             'frac_of_hbm_peak': byt / sk / 1e6 / peak},
             'xty_pass': {'kernel': 'ggp::xty_ts_kernel (B = Y^T X, tcgen05 3xTF32)', 'ms': xt, 'gbs': byt / xt / 1e6,
                          'frac_of_hbm_peak': byt / xt / 1e6 / peak},

@@ -182,7 +182,7 @@ def test_get_y_error_stats_api(cuda):
     assert abs(got['integrated_ci'] - ref['integrated_ci']) <= 5e-5 * abs(ref['integrated_ci'])
 
 
-@pytest.mark.parametrize('n,B', [(1, 3), (4, 7), (31, 5), (32, 5), (33, 5), (100, 6), (256, 9), (300, 3)])
+@pytest.mark.parametrize('n,B', [(1, 3), (4, 7), (31, 5), (32, 5), (33, 5), (100, 6), (256, 9), (300, 3), (1000, 2)])
 def test_chol_draw_matches_numpy_cholesky(cuda, n, B):
     """dev = L z with Sigma = L L^T (the draw step of wPred) against numpy.linalg.cholesky, over block sizes around the
     32-wide panels; entries of a Cholesky factor are unique, so the product must agree to rounding."""
