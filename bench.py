@@ -512,9 +512,12 @@ def sharded_collectives_bench(torch, model, data, rank, world, nsamp=64, npred_t
     clo, chi = gdist.shard_bounds(n, rank, world)
     clo -= clo % 4                                      # keep slabs 16-byte aligned
     Xs = X[:, clo:chi].contiguous()
-    om = np.random.RandomState(3).normal(size=(chi - clo, 25)).astype(np.float32)
+    om = torch.as_tensor(np.random.RandomState(3).normal(size=(chi - clo, 25)).astype(np.float32), device='cuda')   # test matrix resident
     full = timed(lambda: gdist.randomized_svd_sharded(Xs, 25, k=0, q=1, omega_slab=om))
     res['rsvd_sharded'] = {'m': int(m), 'n_y_per_rank': int(chi - clo), 'ms': full,
+                           'note': 'whole decomposition with the slab and the test matrix resident: 4 streaming passes + m x 25 QR, '
+                                   '25 x n Gram, 25 x 25 eigh (torch) + the all_reduces',
+                           'passes_min_ms_at_hbm_peak': 4 * 4.0 * m * (chi - clo) / 6533.8e6,
                            'collective': 'NCCL all_reduce of the (m, 25) float32 sketch per pass (2 passes) + (25, 25) float64 Gram',
                            'gbs_aggregate_4_passes': 4 * 4.0 * m * (chi - clo) * world / full / 1e6}
     return res

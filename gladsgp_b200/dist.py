@@ -59,7 +59,7 @@ def randomized_svd_sharded(X_slab, p, k=None, q=1, omega_slab=None, products=Non
     Returns (U (m, p), S (p,), Vh_slab (p, n_local)) as tensors on X_slab's device.  `omega_slab` is the block of
     rows of the (n, r) Gaussian test matrix that belongs to this slab; to reproduce a single-GPU run every rank
     draws the full matrix from the same seeded np.random stream and slices it (src/svd.py:51 draws it from the
-    global stream).  `products` = (sketch(X, omegaT) -> X @ omegaT.T, xty(X, Y) -> Y.T @ X); default: the
+    global stream); a torch tensor already on the device is used as it is.  `products` = (sketch(X, omegaT) -> X @ omegaT.T, xty(X, Y) -> Y.T @ X); default: the
     tensor-core kernels (ops.rsvd_sketch_tc / ops.rsvd_xty_tc)."""
     import torch
     import torch.distributed as dist
@@ -80,7 +80,10 @@ def randomized_svd_sharded(X_slab, p, k=None, q=1, omega_slab=None, products=Non
     n_local = X_slab.shape[1]
     if omega_slab is None:
         raise ValueError('omega_slab (n_local, r) is required: slice it from the rank-consistent test matrix')
-    omT = torch.as_tensor(np.ascontiguousarray(np.asarray(omega_slab, dtype=np.float32).T), device=X_slab.device)
+    if torch.is_tensor(omega_slab):                           # already on the device: transpose there
+        omT = omega_slab.to(device=X_slab.device, dtype=torch.float32).T.contiguous()
+    else:
+        omT = torch.as_tensor(np.ascontiguousarray(np.asarray(omega_slab, dtype=np.float32).T), device=X_slab.device)
     if omT.shape != (r, n_local):
         raise ValueError('omega_slab must have shape (n_local, p + k)')
     Y = allsum(sketch(X_slab, omT))
