@@ -15,9 +15,6 @@
 
 namespace ggp {
 
-#ifndef GGP_PRED_PF
-#define GGP_PRED_PF 2             // panels of L2 prefetch distance in predict_kernel (0: off)
-#endif
 constexpr int PNT = 256;          // threads of the prediction kernel
 constexpr int PNW = PNT / 32;
 constexpr int PB = 256;           // designs per task: 8 warps x 4 units x 8 rows
@@ -87,19 +84,6 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
             for (int idx = tid; idx < 1024; idx += PNT)
                 sm.Minv[(idx >> 5) * MI_LD + (idx & 31)] = Lp[minv_off(Mp) + 1024LL * j + idx];
             if (tid < 32) sm.uj[tid] = ub[row0 + tid];
-#if GGP_PRED_PF > 0
-            {
-                // L2 prefetch of what panel j + GGP_PRED_PF will read: the rows of that block in the panels before it (2 KB runs,
-                // one per 8-column sub-slab) and its inverted diagonal block.  A call of a few designs keeps one warp of the CTA
-                // busy and is bound by the latency of these first-touch reads (1 MB of factor per block): 0.88 -> ... ms
-                const int jn = j + GGP_PRED_PF;
-                if (jn < nP) {
-                    const double* rows = Lp + (size_t)(32 * jn) * 8;
-                    for (int l = tid; l < 64 * jn; l += PNT) prefetch_l2(rows + soff[l >> 4] + (l & 15) * 16);
-                    if (tid < 64) prefetch_l2(Lp + minv_off(Mp) + 1024LL * jn + tid * 16);
-                }
-            }
-#endif
             __syncthreads();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
