@@ -171,6 +171,45 @@ def test_loglik_large_m_many_inputs(cuda):
         assert abs(ll[b] - ref) <= LL_RTOL * abs(ref)
 
 
+def test_loglik_cfg5_size_against_scipy_and_across_schedules(cuda, monkeypatch):
+    """BASELINE.json configs[4] at full size (m = 4096, d = 17): log-likelihood against SciPy's Cholesky at 1e-8, and the
+    16-CTA cluster schedule (what one chain of 20 PCs runs) bit-identical to the one-CTA look-ahead and plain schedules."""
+    import scipy.linalg
+    from gladsgp_b200 import ops, synthetic, _lib
+    h = _lib.load()
+    m, q = 4096, 16
+    t = synthetic.design(m, q)
+    X = np.concatenate([0.5 * np.ones((m, 1)), t.astype(np.float64)], axis=1)
+    rng = np.random.default_rng(4)
+    beta = np.exp(rng.uniform(np.log(0.05), np.log(1.0), size=(1, q + 1)))
+    lamz = np.array([1.1]); dadd = np.array([3e-3])
+    W = rng.standard_normal((1, m))
+    D = np.zeros((m, m))
+    for k in range(q + 1):
+        D += beta[0, k] * (X[:, None, k] - X[None, :, k]) ** 2
+    C = np.exp(-D) / lamz[0]
+    np.fill_diagonal(C, 1 / lamz[0] + dadd[0])
+    L = scipy.linalg.cholesky(C, lower=True)
+    u = scipy.linalg.solve_triangular(L, W[0], lower=True)
+    ref = -np.sum(np.log(np.diag(L))) - 0.5 * u @ u
+    res = {}
+    old = h.ggp_set_lookahead(1)
+    try:
+        for key, g, la in (('cluster16', '16', 1), ('la', '1', 1), ('plain', '1', 0)):
+            monkeypatch.setenv('GGP_CLUSTER', g)
+            h.ggp_set_lookahead(la)
+            out = ops.loglik_batched(X, W, beta, lamz, dadd, want_u=True)
+            res[key] = (out['loglik'].cpu().numpy(), out['u'].cpu().numpy())
+            assert int(out['info'].cpu().numpy()[0]) == 0
+    finally:
+        h.ggp_set_lookahead(old)
+    assert abs(res['cluster16'][0][0] - ref) <= LL_RTOL * abs(ref)
+    np.testing.assert_allclose(res['cluster16'][1][0, :m], u, rtol=1e-7, atol=1e-9)
+    for key in ('la', 'plain'):
+        for a, b in zip(res['cluster16'], res[key]):
+            assert np.array_equal(a, b), key
+
+
 def test_cluster_and_single_cta_variants_agree_bitwise(cuda, monkeypatch):
     """Small batches run one matrix per thread-block cluster (up to 8 CTAs); the per-unit arithmetic is the same
     as in the one-CTA-per-matrix variant, so results must be bit-identical."""

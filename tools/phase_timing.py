@@ -11,7 +11,7 @@ from gladsgp_b200 import _lib
 _lib.LIB_PATH = so
 from gladsgp_b200 import ops, synthetic
 lib = _lib.load()
-m, q = 512, 8
+m, q = int(os.environ.get('M', 512)), int(os.environ.get('Q', 8))          # M=4096 Q=16 with B=20: the cfg5 shape (16-CTA clusters)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 d = q + 1
 t = synthetic.design(m, q)
@@ -29,9 +29,10 @@ raw.ggp_debug_phase_cycles(buf, 1)
 ops.loglik_batched(Xd, Wd, bd, ld, dd, factor_ws=ws)
 raw.ggp_debug_phase_cycles(buf, 1)
 names = ['fill+sync', 'pair0 gemm+cov', 'wait A', 'factor(w0)/idle', 'wait B0', 'usolve(w0)/minv/idle', 'wait B', 'finish+rest', 'wait C']
-print('precise (data-dependent) serial timers, cycles per panel (16 panels):')
+nP = (m + 31) // 32
+print('precise (data-dependent) serial timers, cycles per panel (%d panels):' % nP)
 for slot, n in ((9, 'w0: other'), (15, 'w0: factor blk0'), (10, 'w0: factor blk1-3'), (11, 'w0: B0 barrier'), (12, 'w0: usolve+store'), (13, 'w1: other'), (14, 'w1: Minv')):
-    print('   %-20s %9.0f' % (n, buf[slot] / 16.0))
+    print('   %-20s %9.0f' % (n, buf[slot] / float(nP)))
 tot2 = sum(buf[i] for i in (20, 21, 22, 23))
 print('worker warp 2 of block 0: total', tot2)
 for slot, n in ((20, 'DMMA update'), (21, 'covariance'), (22, 'TRSM+store'), (23, 'other (barriers, serial wait)')):
