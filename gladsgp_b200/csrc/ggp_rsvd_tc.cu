@@ -413,7 +413,7 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 template <bool FUSE, bool RAWHI, int DRY = 0>      // DRY (developer timing only, wrong results): 1 = no split, 2 = no split, no MMA
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 sketch_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapO, int m, long long n,
-                  int r, int k0, float* __restrict__ partial)
+                  int r, int k0, float* __restrict__ partial, int dry_tiled = 0)
 {
     constexpr int DCOLS = FUSE ? 96 : 32;                       // TMEM columns per 128-row tile and buffer
     constexpr int TCOLS = FUSE ? 512 : TC_TMEM_COLS;            // 2 buffers x 2 tiles x DCOLS, rounded up to a power of two
@@ -464,7 +464,10 @@ sketch_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     unsigned char* st = smem_raw + (size_t)s * TMA_RAW_BYTES;
                     const int c0 = (int)((ch_begin + it) * TC_K);
                     mbar_arrive_expect_tx(&raw_bar[s], (uint32_t)TMA_RAW_BYTES);
-                    tma_load_2d(st, &mapX, c0, row_base, &raw_bar[s]);
+                    // (dry_tiled, DRY runs only: mapX describes the same bytes as contiguous 32 KB tiles -- what a tile-major copy
+                    //  of the ensemble would stream)
+                    if (DRY && dry_tiled) tma_load_2d(st, &mapX, 0, (int)(((long long)blockIdx.y * nchunk + ch_begin + it) * TC_ROWS), &raw_bar[s]);
+                    else tma_load_2d(st, &mapX, c0, row_base, &raw_bar[s]);
                     tma_load_2d(st + TC_A_BYTES, &mapO, c0, k0, &raw_bar[s]);
                 }
             }
@@ -1120,8 +1123,12 @@ int ggp_rsvd_sketch_tc_f32(const float* X, int m, long long n, const float* Omeg
         auto kern = (mode == 1) ? sketch_tma_kernel<false, false> : (mode == 2) ? sketch_tma_kernel<true, false> :
                     (mode == 8) ? sketch_tma_kernel<true, true, 1> : (mode == 9) ? sketch_tma_kernel<true, true, 2> : sketch_tma_kernel<true, true>;
         GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+        int dry_tiled = 0;
+        if (mode >= 8 && getenv("GGP_TMA_TILED") && (long long)m * n % (32LL * TC_ROWS) == 0 && m % TC_ROWS == 0) {
+            dry_tiled = make_tmap_f32(&mapX, X, (long long)m * n / 32, 32, TC_ROWS) ? 1 : 0;
+        }
         for (int k0 = 0; k0 < r; k0 += 32) {
-            kern<<<dim3((unsigned)gx, gy), TMA_THREADS, TMA_SMEM_BYTES, st>>>(mapX, mapO, m, n, r, k0, partial);
+            kern<<<dim3((unsigned)gx, gy), TMA_THREADS, TMA_SMEM_BYTES, st>>>(mapX, mapO, m, n, r, k0, partial, dry_tiled);
             GGP_CUDA(cudaGetLastError());
             tc_reduce_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(partial, (int)gx, m, r, k0, Y_out);
             GGP_CUDA(cudaGetLastError());
