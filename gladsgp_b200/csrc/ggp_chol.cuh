@@ -64,6 +64,13 @@ __device__ unsigned long long g_stage[4 * 64 * 2];  // look-ahead variant, block
 #define GGP_TICKW(w, slot, dep) do { } while (0)
 #endif
 
+// entries of the shared-memory table of the in-kernel exponential (exp_neg below)
+#ifndef GGP_ETAB
+#define GGP_ETAB 64
+#endif
+constexpr int ETAB = GGP_ETAB;
+static_assert(ETAB == 32 || ETAB == 64, "exp table of 32 or 64 entries");
+
 // DMMA steps / shared-memory doubles of the covariance distance product (see pair_cov)
 __host__ __device__ inline int cov_ksteps(int d) { return (d + 5) >> 2; }
 __host__ __device__ inline int sc_doubles(int d) { return 128 * cov_ksteps(d); }
@@ -75,7 +82,7 @@ struct EvalSmem {
     double* rdiag;  // [32]
     double* uj;     // [32]
     double* red;    // [8]
-    double* etab;   // [32] 2^(j/32)
+    double* etab;   // [ETAB] 2^(j/ETAB)
     double* wres;   // [Mp]
     double* sb;     // [d]     sqrt(beta)
     double* SC;     // [sc_doubles(d)] B fragments of the distance product for the current panel's columns
@@ -84,7 +91,7 @@ struct EvalSmem {
 };
 
 __host__ __device__ inline size_t eval_smem_bytes(int Mp, int d) {
-    return (size_t)(32 * D_LD + 32 * LT_LD + 32 * MI_LD + 32 + 32 + 8 + 32 + Mp + (size_t)sc_doubles(d) + ((d + 1) & ~1)) * sizeof(double) + 16 + (size_t)(Mp / 8) * sizeof(int);
+    return (size_t)(32 * D_LD + 32 * LT_LD + 32 * MI_LD + 32 + 32 + 8 + ETAB + Mp + (size_t)sc_doubles(d) + ((d + 1) & ~1)) * sizeof(double) + 16 + (size_t)(Mp / 8) * sizeof(int);
 }
 
 // shared-memory carve-out (percent of 228 KB) that just fits three CTAs: the rest stays L1 so that the
@@ -105,7 +112,7 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     s.rdiag = p;    p += 32;
     s.uj = p;       p += 32;
     s.red = p;      p += 8;
-    s.etab = p;     p += 32;
+    s.etab = p;     p += ETAB;
     s.wres = p;     p += Mp;
     s.SC = p;       p += (size_t)sc_doubles(d);
     s.sb = p;       p += ((d + 1) & ~1);
@@ -114,33 +121,40 @@ __device__ inline EvalSmem carve_eval_smem(unsigned char* base, int Mp, int d) {
     return s;
 }
 
-// exp(y) for y <= 0, ~1 ulp: y = (32 n + j) ln2/32 + r, |r| <= ln2/64, exp(y) = 2^n * 2^(j/32) * p(r).
-// 12 FP64 operations (libdevice exp: ~25) and a fraction of its code size.  Results below 1e-300 flush to 0
-// (covariance entries that small cannot influence any result at 1e-8).
+// exp(y) for y <= 0, ~1 ulp: y = (T n + j) ln2/T + r, |r| <= ln2/(2T), exp(y) = 2^n * 2^(j/T) * p(r), T = ETAB table entries.
+// T = 32: degree 7, 12 FP64 operations (libdevice exp: ~25) and a fraction of its code size; T = 64 (default since round 2):
+// |r| <= 0.0054, the r^6/720 term is below 4e-17, degree 5 is enough: 10 operations on the FP64 pipe the DMMAs share.
+// Results below 1e-300 flush to 0 (covariance entries that small cannot influence any result at 1e-8).
 __device__ __forceinline__ double exp_neg(double y, const double* __restrict__ etab)
 {
-    const double t = fma(y, 46.166241308446828384, 6755399441055744.0);     // 32/ln2, 1.5*2^52
-    const int n32 = __double2loint(t);
+    constexpr double SC = (ETAB == 64) ? 2.0 : 1.0;
+    const double t = fma(y, SC * 46.166241308446828384, 6755399441055744.0);   // T/ln2, 1.5*2^52
+    const int nt = __double2loint(t);
     const double fn = t - 6755399441055744.0;
-    double r = fma(fn, -0.021660849390173098, y);                              // ln2/32 high part (low 20 mantissa bits zero)
-    r = fma(fn, -2.325192846878874e-12, r);                                     // ln2/32 low part
-    double p = 1.9841269841269841e-04;                                          // 1/5040
-    p = fma(p, r, 1.3888888888888889e-03);
-    p = fma(p, r, 8.3333333333333332e-03);
+    double r = fma(fn, -0.021660849390173098 / SC, y);                         // ln2/T high part (low 20 mantissa bits zero)
+    r = fma(fn, -2.325192846878874e-12 / SC, r);                                // ln2/T low part
+    double p;
+    if (ETAB == 64) {
+        p = 8.3333333333333332e-03;                                             // 1/120
+    } else {
+        p = 1.9841269841269841e-04;                                             // 1/5040
+        p = fma(p, r, 1.3888888888888889e-03);
+        p = fma(p, r, 8.3333333333333332e-03);
+    }
     p = fma(p, r, 4.1666666666666664e-02);
     p = fma(p, r, 1.6666666666666666e-01);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const double v = p * etab[n32 & 31];
-    const int n = n32 >> 5;
+    const double v = p * etab[nt & (ETAB - 1)];
+    const int n = nt >> ((ETAB == 64) ? 6 : 5);
     const double res = __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
     return (y < -690.0) ? 0.0 : res;
 }
 
 __device__ inline void fill_exp_table(double* etab)
 {
-    if (threadIdx.x < 32) etab[threadIdx.x] = exp2((double)threadIdx.x * 0.03125);
+    if (threadIdx.x < ETAB) etab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / ETAB));
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -917,7 +931,7 @@ struct LaSmem {
     double* rdiag;  // [32]
     double* uj;     // [2][32]      u blocks (by parity of the block index)
     double* red;    // [8]
-    double* etab;   // [32]
+    double* etab;   // [ETAB]
     double* wres;   // [Mp]
     double* sb;     // [dpad]
     double* SC;     // [2][sc_doubles(d)] B fragments of the distance product (by parity of the panel index)
@@ -929,7 +943,7 @@ struct LaSmem {
 
 __host__ __device__ inline size_t la_smem_bytes(int Mp, int d) {
     const int dpad = (d + 1) & ~1;
-    return (size_t)(32 * MI_LD + 32 * LT_LD + 32 * D_LD + 32 + 64 + 8 + 32 + Mp + dpad + 2 * sc_doubles(d) + NWARP * SCR_DOUBLES) * sizeof(double) +
+    return (size_t)(32 * MI_LD + 32 * LT_LD + 32 * D_LD + 32 + 64 + 8 + ETAB + Mp + dpad + 2 * sc_doubles(d) + NWARP * SCR_DOUBLES) * sizeof(double) +
            16 + (size_t)(Mp / 8) * sizeof(int);
 }
 
@@ -943,7 +957,7 @@ __device__ inline LaSmem carve_la_smem(unsigned char* base, int Mp, int d) {
     s.rdiag = p;    p += 32;
     s.uj = p;       p += 64;
     s.red = p;      p += 8;
-    s.etab = p;     p += 32;
+    s.etab = p;     p += ETAB;
     s.wres = p;     p += Mp;
     s.sb = p;       p += dpad;
     s.SC = p;       p += 2 * sc_doubles(d);

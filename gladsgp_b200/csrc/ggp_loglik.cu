@@ -29,8 +29,8 @@ cov_build_kernel(const double* __restrict__ X, int m, int d, const double* __res
     double* XA = reinterpret_cast<double*>(smem_raw);      // [CT][K4] row side:    [x~, |x~|^2, 1, 0..]
     double* XB = XA + CT * K4;                             // [CT][K4] column side: [2 x~, -1, -|x~|^2, 0..]
     double* T = XB + CT * K4;                              // [CT][CT_LD] the tile
-    double* etab = T + CT * CT_LD;                         // [32]
-    double* sbs = etab + 32;                               // [d] sqrt(beta)
+    double* etab = T + CT * CT_LD;                         // [ETAB]
+    double* sbs = etab + ETAB;                               // [d] sqrt(beta)
     const int b = blockIdx.y;
     // decode lower-triangular tile index
     int t = blockIdx.x;
@@ -151,8 +151,8 @@ cov_build_rows_kernel(const double* __restrict__ X, int m, int d, const double* 
     const int KS = KSC > 0 ? KSC : cov_ksteps(d), K4 = 4 * KS;
     double* XA = reinterpret_cast<double*>(smem_raw);      // [CT][K4] row side:    [x~, |x~|^2, 1, 0..]
     double* XB = XA + CT * K4;                             // [2][CT][K4] column side: [2 x~, -1, -|x~|^2, 0..] (double-buffered)
-    double* etab = XB + 2 * CT * K4;                       // [32]
-    double* sbs = etab + 32;                               // [d] sqrt(beta)
+    double* etab = XB + 2 * CT * K4;                       // [ETAB]
+    double* sbs = etab + ETAB;                             // [d] sqrt(beta)
     const int b = blockIdx.y;
     const int bi = (int)gridDim.x - 1 - (int)blockIdx.x;   // long row blocks first
     const double* be = beta + (size_t)b * d;
@@ -239,8 +239,8 @@ cross_cov_kernel(const double* __restrict__ X, int m, const double* __restrict__
     const int KS = KSC > 0 ? KSC : cov_ksteps(d), K4 = 4 * KS;
     double* XA = reinterpret_cast<double*>(smem_raw);      // [CT][K4] row side:    [x~, |x~|^2, 1, 0..]
     double* XB = XA + CT * K4;                             // [2][CT][K4] column side: [2 x~, -1, -|x~|^2, 0..] (double-buffered)
-    double* etab = XB + 2 * CT * K4;                       // [32]
-    double* sbs = etab + 32;                               // [d]
+    double* etab = XB + 2 * CT * K4;                       // [ETAB]
+    double* sbs = etab + ETAB;                             // [d]
     // CTA = (matrix b, 64-row block, run of ct_per_cta column tiles): prologue and row side once per CTA
     const int runs = (n_ct + ct_per_cta - 1) / ct_per_cta;
     const int per_b = n_rt * runs;
@@ -356,7 +356,7 @@ __global__ void unpack_factor_kernel(const double* __restrict__ Lws, long long l
 // test hook for the in-kernel exponential
 __global__ void exp_neg_kernel(const double* __restrict__ y, double* __restrict__ out, int n)
 {
-    __shared__ double etab[32];
+    __shared__ double etab[ETAB];
     fill_exp_table(etab);
     __syncthreads();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = exp_neg(y[i], etab);
@@ -376,7 +376,7 @@ int ggp_cov_build_f64(const double* X, int m, int d, const double* beta, const d
     cudaStream_t st = (cudaStream_t)stream;
     int nt = (m + CT - 1) / CT;
     int ntile = nt * (nt + 1) / 2;
-    size_t smem = (size_t)(2 * CT * 4 * cov_ksteps(d) + CT * CT_LD + 32 + d) * sizeof(double);
+    size_t smem = (size_t)(2 * CT * 4 * cov_ksteps(d) + CT * CT_LD + ETAB + d) * sizeof(double);
     GGP_ARG(smem <= 200 * 1024, "d too large for cov_build");
     auto run = [&](auto kern) -> int {
         GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -387,7 +387,7 @@ int ggp_cov_build_f64(const double* X, int m, int d, const double* beta, const d
     // whole 64-row blocks and an aligned output: the row-block kernel (GGP_COVROWS=0 keeps the tile kernel)
     const char* env_rows = getenv("GGP_COVROWS");
     if (m % CT == 0 && (reinterpret_cast<uintptr_t>(C_out) & 15) == 0 && !(env_rows && atoi(env_rows) == 0)) {
-        const size_t smem_r = (size_t)(3 * CT * 4 * cov_ksteps(d) + 32 + d) * sizeof(double);
+        const size_t smem_r = (size_t)(3 * CT * 4 * cov_ksteps(d) + ETAB + d) * sizeof(double);
         auto run_rows = [&](auto kern) -> int {
             GGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
             kern<<<dim3(nt, B), 256, smem_r, st>>>(X, m, d, beta, lamz, diag_add, C_out);
@@ -421,7 +421,7 @@ int ggp_cross_cov_f64(const double* X, int m, const double* Xp, int n, int d, co
     GGP_ARG(X && Xp && beta && lamz && S21_out, "null pointer");
     GGP_ARG(m > 0 && n > 0 && d > 0 && B > 0, "m, n, d, B must be positive");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)(3 * CT * 4 * cov_ksteps(d) + 32 + d) * sizeof(double);
+    const size_t smem = (size_t)(3 * CT * 4 * cov_ksteps(d) + ETAB + d) * sizeof(double);
     GGP_ARG(smem <= 200 * 1024, "d too large for cross_cov");
     const int n_ct = (n + CT - 1) / CT, n_rt = (m + CT - 1) / CT;
     // runs of up to 8 column tiles per CTA (prologue and row side amortised), but at least ~4 CTAs per SM slot in total

@@ -22,14 +22,14 @@ constexpr int PB = 256;           // designs per task: 8 warps x 4 units x 8 row
 struct PredSmem {
     double* Minv;   // [32][MI_LD] inverted diagonal block of the current panel (from the packed factor)
     double* uj;     // [32]
-    double* etab;   // [32]
+    double* etab;   // [ETAB]
     double* sb;     // [d]
     double* SC;     // [d][32] scaled training coordinates of the current panel
     double* scr;    // [PNW][16][32] per-warp scratch of the covariance step
 };
 
 __host__ __device__ inline size_t pred_smem_bytes(int d) {
-    return (size_t)(32 * MI_LD + 32 + 32 + sc_doubles(d) + 2 * ((d + 1) & ~1) + PNW * 512) * sizeof(double);
+    return (size_t)(32 * MI_LD + 32 + ETAB + sc_doubles(d) + 2 * ((d + 1) & ~1) + PNW * 512) * sizeof(double);
 }
 
 // One CTA pushes blocks of PB test designs through the cached factor of block b.  Rows = designs: each
@@ -49,7 +49,7 @@ predict_kernel(const double* __restrict__ X, int m, int Mp, int d, const double*
         double* p = reinterpret_cast<double*>(smem_raw);
         sm.Minv = p;  p += 32 * MI_LD;
         sm.uj = p;    p += 32;
-        sm.etab = p;  p += 32;
+        sm.etab = p;  p += ETAB;
         sm.SC = p;    p += sc_doubles(d);
         sm.sb = p;    p += ((d + 1) & ~1);
         sm.scr = p;
