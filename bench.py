@@ -704,7 +704,10 @@ def run_ours(args):
                        'rsvd_setup_s': svd_s, 'setup_s': setup_s},
             'single_chain_equiv_steps_per_s': value / total_chains,
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(d2h),
-                    'api': 'SepiaModel.do_mcmc_chains (host np.random stream -> device, draws -> host)'},
+                    'api': 'SepiaModel.do_mcmc_chains (host np.random stream -> device, draws -> host)',
+                    'note': 'a separate pass of the same K steps (own np.random stream, chains continue from where the device pass '
+                            'left them): the two passes evaluate slightly different numbers of sites (proposals outside the bounds '
+                            'are rejected without an evaluation), hence a few per cent either way'},
             'gpu_launches': args.steps,            # one ggp::sweep_kernel (step kernel) launch per mcmc_step in the timed region
             'roofline': {'bound': 'tensor', 'kernel': 'ggp::sweep_kernel (step kernel: fused cov build + DMMA Cholesky + solve per site, lamWOs terms, close)',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
