@@ -11,6 +11,9 @@ sys.path.insert(0, ROOT)
 if len(sys.argv) > 1 and sys.argv[1] == '--child':
     import numpy as np
     import torch
+    from gladsgp_b200 import _lib
+    if os.environ.get('GGP_LIB'):                      # developer A/B runs against a variant library
+        _lib.LIB_PATH = os.environ['GGP_LIB']
     from gladsgp_b200 import ops
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'chain_cfg3.npz'))
     tb = {k[3:]: g[k] for k in g.files if k.startswith('tb_')}
