@@ -21,6 +21,7 @@ import numpy as np
 
 from .. import ops, _lib
 
+CHOL_DRAW_MAX_N = 16384   # ggp_chol_draw_f64 keeps an n-vector and n/8 offsets in shared memory
 MAX_JOINT = 1024      # above this many designs per call the joint covariance is not formed unless joint=True is passed
 
 
@@ -181,9 +182,13 @@ class SepiaEmulatorPrediction(SepiaPrediction):
                 # realisation = mean + F z with F F^T = Sigma.  Sigma >= I / lamWs is positive definite, so the factor is a
                 # Cholesky factor (SEPIA uses U sqrt(s) of an SVD: the same distribution; neither is bit-comparable across
                 # implementations); the eigen-factor stays as the fall-back when a block is rejected (info != 0)
-                dev, info = ops.chol_draw(Sig, zd.reshape(ns * pu, npred))
-                dev = dev.reshape(ns, pu, npred)
-                self.launches += 1
+                if npred <= CHOL_DRAW_MAX_N:
+                    dev, info = ops.chol_draw(Sig, zd.reshape(ns * pu, npred))
+                    dev = dev.reshape(ns, pu, npred)
+                    self.launches += 1
+                else:                         # beyond the kernel's shared-memory limit (explicit joint=True on a very large call)
+                    L, info = torch.linalg.cholesky_ex(Sig.reshape(ns, pu, npred, npred))
+                    dev = torch.matmul(L, zd.unsqueeze(-1)).squeeze(-1)
                 bad = _pinned(eng, 'bad', 1)
                 bad.copy_((info != 0).any().to(torch.float64).reshape(1), non_blocking=True)
             else:
