@@ -3,7 +3,10 @@ import json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from gladsgp_b200 import ops, _lib
+from gladsgp_b200 import _lib
+if os.environ.get('GGP_LIB'):                      # developer A/B runs against a variant library
+    _lib.LIB_PATH = os.environ['GGP_LIB']
+from gladsgp_b200 import ops
 m, n, r = 512, 1460000, 25
 g = torch.Generator(device='cuda'); g.manual_seed(0)
 X = torch.randn((m, n), dtype=torch.float32, device='cuda', generator=g)
