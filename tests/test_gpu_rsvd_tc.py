@@ -139,3 +139,30 @@ def test_tma_fed_xty_matches_float64_and_tmem_kernel(cuda, monkeypatch, m, n, r)
     assert np.abs(got - truth).max() <= 1e-6 * np.abs(truth).max()
     assert np.abs(got - ref).max() <= 2e-6 * np.abs(truth).max()
     assert np.array_equal(got, ops.rsvd_xty_tc(Xd, Yd).cpu().numpy())
+
+
+@pytest.mark.parametrize('m,n', [(512, 1460000), (1100, 1200004)])
+def test_passes_at_full_ensemble_size_against_float64(cuda, m, n):
+    """BASELINE.json cfg3 at full size (512 x 1.46 M float32, 3 GB) and an ensemble beyond 4 GB (byte offsets above 2^32): both
+    passes against float64 products formed on the device in column chunks; inputs generated on the device."""
+    import torch
+    from gladsgp_b200 import ops
+    r = 25
+    g = torch.Generator(device='cuda'); g.manual_seed(m)
+    X = torch.randn((m, n), dtype=torch.float32, device='cuda', generator=g)
+    X *= torch.rand((1, n), dtype=torch.float32, device='cuda', generator=g) * 2.9 + 0.1
+    Om = torch.randn((r, n), dtype=torch.float32, device='cuda', generator=g)
+    Yh = torch.randn((m, r), dtype=torch.float32, device='cuda', generator=g)
+    got = ops.rsvd_sketch_tc(X, Om).double()
+    gotb = ops.rsvd_xty_tc(X, Yh)
+    ref = torch.zeros((m, r), dtype=torch.float64, device='cuda')
+    errb, scaleb = 0.0, 0.0
+    step = 100000
+    for c0 in range(0, n, step):
+        Xc = X[:, c0:c0 + step].double()
+        ref += Xc @ Om[:, c0:c0 + step].double().T
+        rb = Yh.double().T @ Xc
+        errb = max(errb, float((gotb[:, c0:c0 + step].double() - rb).abs().max()))
+        scaleb = max(scaleb, float(rb.abs().max()))
+    assert float((got - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    assert errb <= 1e-6 * scaleb
