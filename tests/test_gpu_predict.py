@@ -221,3 +221,38 @@ def test_chol_draw_chunked_workspace_and_rejection(cuda, monkeypatch):
     assert np.array_equal(dev1.cpu().numpy()[good], dev2.cpu().numpy()[good])
     ref = np.einsum('bij,bj->bi', np.linalg.cholesky(Sig[good]), z[good])
     np.testing.assert_allclose(dev1.cpu().numpy()[good], ref, rtol=1e-10, atol=1e-12)
+
+
+def test_full_size_prediction_is_invariant_to_the_call_split(cuda):
+    """cfg4 shape (m = 512, pu = 10) at 20 000 designs per call: moments are bit-identical whether the designs go through in
+    one call, in the reference's 4-design calls or in ragged pieces (size-independent property at a size the oracle
+    cannot reach), and the variances stay within (0, s11]."""
+    from gladsgp_b200 import ops
+    pr = make_problem(m=512, q=8, pu=10)
+    num = pr['num']
+    samples = synthetic.posterior_samples(4, num.d, 10, seed=21)
+    n = 20000
+    tp = synthetic.test_design(n, 8)
+    xp = np.concatenate([0.5 * np.ones((n, 1)), tp.astype(np.float64)], axis=1)
+    beta, lamz, dadd, s11, W = _blocks(num, samples)
+    P = ops.Predictor(num.zt, W, beta, lamz, dadd, s11)
+    mean, var = (a.cpu().numpy() for a in P.predict(xp))
+    assert np.isfinite(mean).all() and (var > 0).all() and (var <= s11[:, None] * (1 + 1e-12)).all()
+    for lo, hi in ((0, 4), (4, 8), (9996, 10000), (255, 769), (19999, 20000), (12345, 13370)):
+        m2, v2 = (a.cpu().numpy() for a in P.predict(xp[lo:hi]))
+        assert np.array_equal(mean[:, lo:hi], m2) and np.array_equal(var[:, lo:hi], v2), (lo, hi)
+
+
+def test_full_size_reconstruction(cuda):
+    """get_y at the full field size of cfg3 / cfg4 (n_y = 1 460 000), 256 rows: against the float32 expression on the device."""
+    import torch
+    from gladsgp_b200 import ops
+    g = torch.Generator(device='cuda'); g.manual_seed(9)
+    R, pu, n_y = 256, 10, 1460000
+    w = torch.randn((R, pu), dtype=torch.float32, device='cuda', generator=g)
+    K = torch.randn((pu, n_y), dtype=torch.float32, device='cuda', generator=g)
+    sd = torch.rand((n_y,), dtype=torch.float32, device='cuda', generator=g) * 1.9 + 0.1
+    mu = torch.randn((n_y,), dtype=torch.float32, device='cuda', generator=g)
+    y = ops.reconstruct(w, K, sd, mu)
+    ref = (w.double() @ K.double()) * sd.double() + mu.double()
+    assert float((y.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
