@@ -87,6 +87,46 @@ def test_all_proposals_out_of_bounds_consume_one_uniform_per_site(cuda):
     np.testing.assert_array_equal(out['draws'].cpu().numpy()[:, 0, :], np.tile(tb['theta'], (3, 1)))
 
 
+@pytest.mark.parametrize('chains', [1, 3, 160])
+def test_candidate_with_a_failing_cholesky_is_rejected_inside_the_sampler(cuda, chains):
+    """SEPIA: a covariance that is not positive definite gives log-lik -inf, i.e. the proposal is rejected and the sweep goes
+    on.  Replayed candidates that break the factorisation (negative lamUz; a negative nugget through lamWs) must leave
+    exactly the chain of a run in which those proposals were marked invalid -- for one chain (cluster / speculative
+    kernels), a few chains (cluster step kernel) and many (look-ahead step kernel)."""
+    from helpers import make_problem, tables_from_oracle, replay_from_trace, so
+    from gladsgp_b200 import ops
+    pr = make_problem(m=100, q=3, pu=2)
+    num = pr['num']
+    om = so.OracleModel(num)
+    tb = tables_from_oracle(om)
+    P = tb['theta'].size
+    d, pu = num.d, 2
+    om.trace = []
+    om.do_mcmc(4, rng=np.random.RandomState(3))
+    replay, _ = replay_from_trace(om.trace, 4, P)
+    bad = {k: v.copy() for k, v in replay.items()}
+    off = {k: v.copy() for k, v in replay.items()}
+    sites = [(1, d * pu + 1, -3.0),            # step 1: lamUz of PC 1 negative -> negative definite covariance
+             (2, d * pu + pu + 0, -1.0e-3)]    # step 2: lamWs of PC 0 -> nugget 1/lamWs = -1000
+    for t, s_, val in sites:
+        bad['cand'][t, 0, s_] = val; bad['valid'][t, 0, s_] = 1; bad['logu'][t, 0, s_] = -1e300; bad['logacorr'][t, 0, s_] = 0.0
+        off['valid'][t, 0, s_] = 0
+    res = []
+    for rp in (bad, off):
+        rpc = {k: np.repeat(v, chains, axis=1) for k, v in rp.items()}
+        eng = ops.McmcEngine(num.zt, num.w.T.copy(), num.LamSim, tb, n_chains=chains)
+        eng.set_state(tb['theta'])
+        out = eng.run(4, tb['step'], replay=rpc, record_accept=True)
+        res.append((out['draws'].cpu().numpy(), out['accepted'].cpu().numpy(), out['lp'].cpu().numpy()))
+    assert np.isfinite(res[0][2]).all()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    for t, s_, _ in sites:
+        assert not res[0][1][t, :, s_].any()
+    for c in range(1, chains):
+        assert np.array_equal(res[0][0][:, c], res[0][0][:, 0])
+
+
 def test_c_abi_reports_errors(cuda):
     """Bad arguments and short workspaces come back as error codes with a message; nothing is thrown across the ABI."""
     import torch
