@@ -256,3 +256,24 @@ def test_full_size_reconstruction(cuda):
     y = ops.reconstruct(w, K, sd, mu)
     ref = (w.double() @ K.double()) * sd.double() + mu.double()
     assert float((y.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+def test_scalar_gp_cfg2_size_10000_designs_against_oracle(cuda):
+    """BASELINE.json configs[1]: 1-D GP with 1000 training points, 10 000 test designs in one call; moments of 60 designs
+    spread over the call against the oracle's SEPIA-style solve (one fresh S22 factorisation per sample)."""
+    from gladsgp_b200 import ops
+    pr = make_scalar_problem(m=1000)
+    num = pr['num']
+    samples = synthetic.posterior_samples(3, num.d, 1, seed=12)
+    samples['betaU'] = np.clip(samples['betaU'], 0.5, None) * 10.0           # length scales that resolve x sin(2 pi x)
+    npred = 10000
+    tp = np.linspace(0.0, 1.0, npred)[:, None]
+    beta, lamz, dadd, s11, W = _blocks(num, samples)
+    P = ops.Predictor(num.zt, W, beta, lamz, dadd, s11)
+    xp = np.concatenate([0.5 * np.ones((npred, 1)), tp], axis=1)
+    mean, var = (a.cpu().numpy() for a in P.predict(xp))
+    idx = np.unique(np.concatenate([np.arange(0, npred, 173), [npred - 1]]))[:60]
+    _, mu, Sig = so.w_pred(num, tp[idx], samples, draw=False)
+    for s in range(3):
+        np.testing.assert_allclose(mean[s, idx], mu[s], rtol=PRED_RTOL, atol=PRED_RTOL * np.abs(mu).max())
+        np.testing.assert_allclose(var[s, idx], np.diag(Sig[s]), rtol=PRED_RTOL, atol=1e-9)
